@@ -1,0 +1,633 @@
+// Tap-list implicit-GEMM convolution (forward / data-gradient) and its weight gradient on the
+// sm_100a tensor cores: TMA (tiled, zero-filled halos) -> shared memory -> tcgen05.mma -> TMEM ->
+// tcgen05.ld epilogue.  One persistent CTA per SM, three roles: warp 0 TMA producer, warp 1 MMA
+// issuer (+ TMEM owner), warps 2..5 epilogue.  TMEM holds two accumulator stages so the epilogue
+// of tile i overlaps the main loop of tile i+1.
+//
+// Geometry: an M tile is 128 output pixels = a BN x BH x BW brick of the NHWC output grid; for a
+// tap (dy,dx) the A operand is the same brick of the source view shifted by (dy,dx), which a 4-D
+// tiled tensor map delivers as 128 rows of BK channels in the canonical K-major swizzled layout
+// (out-of-range rows/columns arrive as zeros = the convolution's zero padding).
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace dfgan {
+
+constexpr int kConvThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 27;
+
+struct ConvMaps {
+  CUtensorMap a[DFGAN_MAX_SRC];
+  CUtensorMap b;
+};
+
+struct ConvK {
+  int n_taps, n_chunks;
+  int tap_src[DFGAN_MAX_TAPS], tap_dy[DFGAN_MAX_TAPS], tap_dx[DFGAN_MAX_TAPS],
+      tap_wrow[DFGAN_MAX_TAPS];
+  int lbw, lbh;  // log2(BW), log2(BH); BN = 128 >> (lbw + lbh)
+  int tiles_w, tiles_h, tiles_n;
+  int n_tiles_n, total_tiles;
+  int n_tile;
+  int N, H, W, Cout;
+  uint32_t idesc;
+  int n_stages;
+  uint32_t a_bytes, b_bytes, tmem_cols;
+  __nv_bfloat16* out;
+  long long out_sw, out_sh, out_sn;
+  const float* bias;
+  const float* scale_dev;
+  float scale_imm;
+  int lrelu_pre;
+  float slope;
+  __nv_bfloat16* aux;
+  const __nv_bfloat16* addend;
+  long long add_sw, add_sh, add_sn;
+  int add_shift;
+  float add_scale;
+  const __nv_bfloat16* mask_src;
+};
+
+__device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n_stages) {
+    if (++stage == n_stages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+template <int BK>
+__global__ void __launch_bounds__(kConvThreads, 1)
+    conv_umma_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.n_stages) * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.n_stages;
+  uint64_t* tfull = bars + 2 * p.n_stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DFGAN_MAX_SRC; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int BW = 1 << p.lbw, BH = 1 << p.lbh;
+  const int k_iters = p.n_taps * p.n_chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        const int tw = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tn = mt / p.tiles_h;
+        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn * (128 >> (p.lbw + p.lbh));
+        for (int t = 0; t < p.n_taps; ++t) {
+          const CUtensorMap* ma = &maps.a[p.tap_src[t]];
+          const int wy = h0 + p.tap_dy[t], wx = w0 + p.tap_dx[t];
+          const int brow = p.tap_wrow[t] + nt * p.n_tile;
+          for (int c = 0; c < p.n_chunks; ++c) {
+            wait_bounded(&empty[ps.stage], ps.phase ^ 1);
+            uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
+            mbar_expect_tx(&full[ps.stage], stage_bytes);
+            tma_load_4d(sa, ma, &full[ps.stage], c * BK, wx, wy, n0);
+            tma_load_2d(sa + p.a_bytes, &maps.b, &full[ps.stage], c * BK, brow);
+            ps.advance(p.n_stages);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    PipeState ps;
+    int as = 0;
+    uint32_t aphase = 0;
+    constexpr uint32_t swz = (BK == 64) ? SWZ_128B : SWZ_64B;
+    constexpr uint32_t sbo = 8u * BK * 2u;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      wait_bounded(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      for (int it = 0; it < k_iters; ++it) {
+        wait_bounded(&full[ps.stage], ps.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
+          const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, swz);
+          const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, sbo, swz);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0);
+          umma_commit(&empty[ps.stage]);
+        }
+        __syncwarp();
+        ps.advance(p.n_stages);
+      }
+      if (lane == 0) umma_commit(&tfull[as]);
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int bw = row & (BW - 1);
+    const int bh = (row >> p.lbw) & (BH - 1);
+    const int bn = row >> (p.lbw + p.lbh);
+    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tn = mt / p.tiles_h;
+      const int w = (tw << p.lbw) + bw, h = (th << p.lbh) + bh;
+      const int n = tn * (128 >> (p.lbw + p.lbh)) + bn;
+      const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+      const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+      const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
+                                          (w >> p.add_shift) * p.add_sw)
+                                       : 0;
+      wait_bounded(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      for (int c = 0; c < p.n_tile; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        const int col = nt * p.n_tile + c;
+        if (valid && col < p.Cout) {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + col + i);
+          }
+          if (p.lrelu_pre) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+          }
+          if (p.aux) {
+            uint4 s0, s1;
+            s0.x = pack_bf16x2(v[0], v[1]), s0.y = pack_bf16x2(v[2], v[3]);
+            s0.z = pack_bf16x2(v[4], v[5]), s0.w = pack_bf16x2(v[6], v[7]);
+            s1.x = pack_bf16x2(v[8], v[9]), s1.y = pack_bf16x2(v[10], v[11]);
+            s1.z = pack_bf16x2(v[12], v[13]), s1.w = pack_bf16x2(v[14], v[15]);
+            uint4* dst = reinterpret_cast<uint4*>(p.aux + o_off + col);
+            dst[0] = s0;
+            dst[1] = s1;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= scale;
+          if (p.addend) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.addend + a_off + col);
+            const uint4 s0 = __ldg(src), s1 = __ldg(src + 1);
+            const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a, b;
+              unpack_bf16x2(u[i], a, b);
+              v[2 * i] += p.add_scale * a;
+              v[2 * i + 1] += p.add_scale * b;
+            }
+          }
+          if (p.mask_src) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.mask_src + o_off + col);
+            const uint4 s0 = __ldg(src), s1 = __ldg(src + 1);
+            const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a, b;
+              unpack_bf16x2(u[i], a, b);
+              v[2 * i] *= (a > 0.f ? 1.f : p.slope);
+              v[2 * i + 1] *= (b > 0.f ? 1.f : p.slope);
+            }
+          }
+          uint4 s0, s1;
+          s0.x = pack_bf16x2(v[0], v[1]), s0.y = pack_bf16x2(v[2], v[3]);
+          s0.z = pack_bf16x2(v[4], v[5]), s0.w = pack_bf16x2(v[6], v[7]);
+          s1.x = pack_bf16x2(v[8], v[9]), s1.y = pack_bf16x2(v[10], v[11]);
+          s1.z = pack_bf16x2(v[12], v[13]), s1.w = pack_bf16x2(v[14], v[15]);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + o_off + col);
+          dst[0] = s0;
+          dst[1] = s1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight gradient.  D[(tap,ci) x co] += sum_pixels X_shifted[pixel,(tap,ci)] * G[pixel,co]; both
+// operands are MN-major (channels contiguous, the pixel index is the GEMM K), split-K over pixel
+// tiles, fp32 atomics into the gradient tensor.
+struct WgradMaps {
+  CUtensorMap a[DFGAN_MAX_SRC];
+  CUtensorMap g;
+};
+
+struct WgradK {
+  int n_taps;
+  int tap_src[DFGAN_MAX_TAPS], tap_dy[DFGAN_MAX_TAPS], tap_dx[DFGAN_MAX_TAPS],
+      tap_id[DFGAN_MAX_TAPS];
+  int lbw, lbh;
+  int tiles_w, tiles_h, tiles_n, pix_tiles;
+  int cb, lcb;          // channels per A row block (64 or 32), log2
+  int blocks_per_tap;   // Cin / cb
+  int row_blocks;       // n_taps * blocks_per_tap
+  int cbg;              // channels per B block
+  int n_tile, n_blocks_b;
+  int n_tiles_m, n_tiles_n, k_splits, total_items;
+  int Cin, Cout;
+  uint32_t idesc;
+  int n_stages;
+  uint32_t a_bytes, b_bytes, a_blk_bytes, b_blk_bytes, tmem_cols;
+  float* dw;
+  long long s_co, s_ci, s_tap;
+  const float* scale_dev;
+  float scale_imm;
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+    wgrad_umma_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ WgradK p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.n_stages) * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.n_stages;
+  uint64_t* tfull = bars + 2 * p.n_stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DFGAN_MAX_SRC; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.g);
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int blocks_per_tile = 128 >> p.lcb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int ks = item % p.k_splits;
+        int r = item / p.k_splits;
+        const int nt = r % p.n_tiles_n;
+        const int mt = r / p.n_tiles_n;
+        const int pt0 = static_cast<int>((static_cast<long long>(p.pix_tiles) * ks) / p.k_splits);
+        const int pt1 =
+            static_cast<int>((static_cast<long long>(p.pix_tiles) * (ks + 1)) / p.k_splits);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          int m = pt;
+          const int tw = m % p.tiles_w;
+          m /= p.tiles_w;
+          const int th = m % p.tiles_h;
+          const int tn = m / p.tiles_h;
+          const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn * (128 >> (p.lbw + p.lbh));
+          wait_bounded(&empty[ps.stage], ps.phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
+          mbar_expect_tx(&full[ps.stage], stage_bytes);
+          for (int b = 0; b < blocks_per_tile; ++b) {
+            int rb = mt * blocks_per_tile + b;
+            if (rb >= p.row_blocks) rb = mt * blocks_per_tile;  // padding block: reload a valid one
+            const int t = rb / p.blocks_per_tap;
+            const int c0 = (rb % p.blocks_per_tap) << p.lcb;
+            tma_load_4d(sa + b * p.a_blk_bytes, &maps.a[p.tap_src[t]], &full[ps.stage], c0,
+                        w0 + p.tap_dx[t], h0 + p.tap_dy[t], n0);
+          }
+          for (int b = 0; b < p.n_blocks_b; ++b)
+            tma_load_4d(sa + p.a_bytes + b * p.b_blk_bytes, &maps.g, &full[ps.stage],
+                        nt * p.n_tile + b * p.cbg, w0, h0, n0);
+          ps.advance(p.n_stages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    PipeState ps;
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint32_t swz_a = (p.cb == 64) ? SWZ_128B : SWZ_64B;
+    const uint32_t swz_b = (p.cbg == 64) ? SWZ_128B : SWZ_64B;
+    const uint32_t sbo_a = 8u * p.cb * 2u, sbo_b = 8u * p.cbg * 2u;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int ks = item % p.k_splits;
+      const int pt0 = static_cast<int>((static_cast<long long>(p.pix_tiles) * ks) / p.k_splits);
+      const int pt1 =
+          static_cast<int>((static_cast<long long>(p.pix_tiles) * (ks + 1)) / p.k_splits);
+      wait_bounded(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      for (int pt = pt0; pt < pt1; ++pt) {
+        wait_bounded(&full[ps.stage], ps.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
+          const uint64_t adesc = make_smem_desc(a_addr, p.a_blk_bytes, sbo_a, swz_a);
+          const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.b_blk_bytes, sbo_b, swz_b);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // 16 pixels per MMA = two 8-pixel swizzle atoms
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>((2u * sbo_a * k) >> 4),
+                      bdesc + static_cast<uint64_t>((2u * sbo_b * k) >> 4), p.idesc,
+                      (pt > pt0) || (k != 0));
+          umma_commit(&empty[ps.stage]);
+        }
+        __syncwarp();
+        ps.advance(p.n_stages);
+      }
+      if (lane == 0) umma_commit(&tfull[as]);
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int r = item / p.k_splits;
+      const int nt = r % p.n_tiles_n;
+      const int mt = r / p.n_tiles_n;
+      const int rb = mt * blocks_per_tile + (row >> p.lcb);
+      const bool valid = rb < p.row_blocks;
+      const int t = valid ? rb / p.blocks_per_tap : 0;
+      const int ci = ((rb % p.blocks_per_tap) << p.lcb) + (row & (p.cb - 1));
+      float* dst = p.dw + ci * p.s_ci + p.tap_id[t] * p.s_tap;
+      wait_bounded(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      for (int c = 0; c < p.n_tile; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        const int col = nt * p.n_tile + c;
+        if (valid && col < p.Cout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + (col + i) * p.s_co, v[i] * scale);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+static void brick_geometry(int W, int H, int& lbw, int& lbh) {
+  int bw = 1;
+  while (bw < W && bw < 16) bw <<= 1;
+  int bh = 1;
+  while (bh < H && bw * bh < 128) bh <<= 1;
+  lbw = ilog2(bw);
+  lbh = ilog2(bh);
+}
+
+static uint32_t pow2_cols(int c) {
+  uint32_t v = 32;
+  while (v < static_cast<uint32_t>(c)) v <<= 1;
+  return v;
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
+}  // namespace dfgan
+
+using namespace dfgan;
+
+extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || !d->out || !d->wpack) return DFGAN_E_ARG;
+  if (d->n_src < 1 || d->n_src > DFGAN_MAX_SRC || d->n_taps < 1 || d->n_taps > DFGAN_MAX_TAPS)
+    return DFGAN_E_ARG;
+  if (d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1) return DFGAN_E_SHAPE;
+  const int BK = (d->Cin % 64 == 0) ? 64 : 32;
+  int n_tile = d->n_tile_hint > 0 ? d->n_tile_hint : (d->Cout <= 256 ? d->Cout : 256);
+  if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return DFGAN_E_SHAPE;
+
+  ConvK k{};
+  ConvMaps maps{};
+  brick_geometry(d->W, d->H, k.lbw, k.lbh);
+  const int BW = 1 << k.lbw, BH = 1 << k.lbh, BN = 128 / (BW * BH);
+  k.tiles_w = (d->W + BW - 1) / BW;
+  k.tiles_h = (d->H + BH - 1) / BH;
+  k.tiles_n = (d->N + BN - 1) / BN;
+  k.n_tiles_n = (d->Cout + n_tile - 1) / n_tile;
+  k.total_tiles = k.tiles_w * k.tiles_h * k.tiles_n * k.n_tiles_n;
+  k.n_tile = n_tile;
+  k.N = d->N, k.H = d->H, k.W = d->W, k.Cout = d->Cout;
+  k.n_taps = d->n_taps;
+  k.n_chunks = d->Cin / BK;
+  for (int t = 0; t < d->n_taps; ++t) {
+    if (d->taps[t].src < 0 || d->taps[t].src >= d->n_src) return DFGAN_E_ARG;
+    k.tap_src[t] = d->taps[t].src;
+    k.tap_dy[t] = d->taps[t].dy;
+    k.tap_dx[t] = d->taps[t].dx;
+    k.tap_wrow[t] = d->taps[t].wrow;
+  }
+  k.idesc = make_idesc_bf16(128, n_tile, 0, 0);
+  k.a_bytes = 128u * BK * 2u;
+  k.b_bytes = static_cast<uint32_t>(n_tile) * BK * 2u;
+  int stages = static_cast<int>(kSmemBudget / (k.a_bytes + k.b_bytes));
+  if (stages > 8) stages = 8;
+  if (stages < 2) return DFGAN_E_SHAPE;
+  k.n_stages = stages;
+  k.tmem_cols = pow2_cols(2 * n_tile);
+  k.out = static_cast<__nv_bfloat16*>(d->out);
+  k.out_sw = d->out_sw, k.out_sh = d->out_sh, k.out_sn = d->out_sn;
+  k.bias = d->bias, k.scale_dev = d->scale_dev, k.scale_imm = d->scale_imm;
+  k.lrelu_pre = d->lrelu_pre, k.slope = d->slope;
+  k.aux = static_cast<__nv_bfloat16*>(d->aux);
+  k.addend = static_cast<const __nv_bfloat16*>(d->addend);
+  k.add_sw = d->add_sw, k.add_sh = d->add_sh, k.add_sn = d->add_sn;
+  k.add_shift = d->add_shift, k.add_scale = d->add_scale;
+  k.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
+
+  for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
+    const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
+    if (v.C != d->Cin) return DFGAN_E_SHAPE;
+    int rc = make_map_nhwc(&maps.a[s], v, BK, BW, BH, BN);
+    if (rc) return rc;
+  }
+  int rc = make_map_2d(&maps.b, d->wpack, d->w_rows, d->Cin, BK, n_tile);
+  if (rc) return rc;
+
+  const size_t smem = static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 1024 + 256;
+  int grid = k.total_tiles;
+  const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
+  if (grid > cap) grid = cap;
+  cudaError_t e;
+  if (BK == 64) {
+    e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    conv_umma_kernel<64><<<grid, kConvThreads, smem, stream>>>(maps, k);
+  } else {
+    e = cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    conv_umma_kernel<32><<<grid, kConvThreads, smem, stream>>>(maps, k);
+  }
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || !d->dw || !d->g.ptr) return DFGAN_E_ARG;
+  if (d->n_src < 1 || d->n_src > DFGAN_MAX_SRC || d->n_taps < 1 || d->n_taps > DFGAN_MAX_TAPS)
+    return DFGAN_E_ARG;
+  if (d->Cin % 32 || d->Cout % 32 || d->g.C != d->Cout) return DFGAN_E_SHAPE;
+
+  WgradK k{};
+  WgradMaps maps{};
+  const int W = d->g.W, H = d->g.H, N = d->g.N;
+  brick_geometry(W, H, k.lbw, k.lbh);
+  const int BW = 1 << k.lbw, BH = 1 << k.lbh, BN = 128 / (BW * BH);
+  k.tiles_w = (W + BW - 1) / BW;
+  k.tiles_h = (H + BH - 1) / BH;
+  k.tiles_n = (N + BN - 1) / BN;
+  k.pix_tiles = k.tiles_w * k.tiles_h * k.tiles_n;
+  k.n_taps = d->n_taps;
+  for (int t = 0; t < d->n_taps; ++t) {
+    if (d->taps[t].src < 0 || d->taps[t].src >= d->n_src) return DFGAN_E_ARG;
+    k.tap_src[t] = d->taps[t].src;
+    k.tap_dy[t] = d->taps[t].dy;
+    k.tap_dx[t] = d->taps[t].dx;
+    k.tap_id[t] = d->taps[t].wrow;
+  }
+  k.cb = (d->Cin % 64 == 0) ? 64 : 32;
+  k.lcb = ilog2(k.cb);
+  k.blocks_per_tap = d->Cin / k.cb;
+  k.row_blocks = d->n_taps * k.blocks_per_tap;
+  k.cbg = (d->Cout % 64 == 0) ? 64 : 32;
+  k.n_tile = d->Cout <= 256 ? d->Cout : 256;
+  if (k.n_tile % k.cbg) return DFGAN_E_SHAPE;
+  k.n_blocks_b = k.n_tile / k.cbg;
+  const int blocks_per_tile = 128 / k.cb;
+  k.n_tiles_m = (k.row_blocks + blocks_per_tile - 1) / blocks_per_tile;
+  k.n_tiles_n = (d->Cout + k.n_tile - 1) / k.n_tile;
+  const int base_items = k.n_tiles_m * k.n_tiles_n;
+  int ks = d->k_splits;
+  if (ks <= 0) {
+    ks = (2 * num_sms() + base_items - 1) / base_items;
+    // keep at least 4 pixel tiles per split so the accumulate chain amortises the epilogue
+    int max_ks = k.pix_tiles / 4;
+    if (max_ks < 1) max_ks = 1;
+    if (ks > max_ks) ks = max_ks;
+  }
+  if (ks > k.pix_tiles) ks = k.pix_tiles;
+  if (ks < 1) ks = 1;
+  k.k_splits = ks;
+  k.total_items = base_items * ks;
+  k.Cin = d->Cin, k.Cout = d->Cout;
+  k.idesc = make_idesc_bf16(128, k.n_tile, 1, 1);
+  k.a_blk_bytes = 128u * k.cb * 2u;
+  k.a_bytes = k.a_blk_bytes * blocks_per_tile;  // always 32 KiB
+  k.b_blk_bytes = 128u * k.cbg * 2u;
+  k.b_bytes = k.b_blk_bytes * k.n_blocks_b;
+  int stages = static_cast<int>(kSmemBudget / (k.a_bytes + k.b_bytes));
+  if (stages > 6) stages = 6;
+  if (stages < 2) return DFGAN_E_SHAPE;
+  k.n_stages = stages;
+  k.tmem_cols = pow2_cols(2 * k.n_tile);
+  k.dw = d->dw;
+  k.s_co = d->s_co, k.s_ci = d->s_ci, k.s_tap = d->s_tap;
+  k.scale_dev = d->scale_dev, k.scale_imm = d->scale_imm;
+
+  for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
+    const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
+    if (v.C != d->Cin) return DFGAN_E_SHAPE;
+    int rc = make_map_nhwc(&maps.a[s], v, k.cb, BW, BH, BN);
+    if (rc) return rc;
+  }
+  int rc = make_map_nhwc(&maps.g, d->g, k.cbg, BW, BH, BN);
+  if (rc) return rc;
+
+  const size_t smem = static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 1024 + 256;
+  int grid = k.total_items;
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  wgrad_umma_kernel<<<grid, kConvThreads, smem, stream>>>(maps, k);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}

@@ -1,0 +1,74 @@
+#include "host_common.h"
+
+#include <mutex>
+
+namespace dfgan {
+
+std::atomic<uint64_t> g_launches{0};
+
+encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  });
+  return fn;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static CUtensorMapSwizzle swizzle_for(int bc) {
+  return bc * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                       : (bc * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+int make_map_nhwc(CUtensorMap* m, const dfgan_view4& v, int bc, int bw, int bh, int bn) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return DFGAN_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) || (v.sw & 7) || (v.sh & 7) || (v.sn & 7))
+    return DFGAN_E_ARG;
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DFGAN_OK : DFGAN_E_DRIVER;
+}
+
+int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int bc, int brows) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return DFGAN_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols & 7)) return DFGAN_E_ARG;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bc, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DFGAN_OK : DFGAN_E_DRIVER;
+}
+
+}  // namespace dfgan
+
+extern "C" {
+int dfgan_version(void) { return 100; }
+const char* dfgan_arch(void) { return "sm_100a"; }
+uint64_t dfgan_launch_count(void) { return dfgan::g_launches.load(); }
+}

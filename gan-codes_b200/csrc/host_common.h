@@ -1,0 +1,43 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/dfgan_b200.h"
+
+namespace dfgan {
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// cuTensorMapEncodeTiled resolved through the runtime so the library carries no link-time
+// dependency on libcuda (it must load on a CPU-only box for the export test).
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode_tiled();
+
+int num_sms();
+
+// bf16 NHWC view -> 4-D tiled tensor map with box {bc, bw, bh, bn}; OOB elements read as zero.
+int make_map_nhwc(CUtensorMap* m, const dfgan_view4& v, int bc, int bw, int bh, int bn);
+// bf16 row-major matrix [rows][cols] -> 2-D tiled tensor map with box {bc, brows}.
+int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int bc, int brows);
+
+inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+#define DFGAN_CUDA_CHECK_LAUNCH()                  \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    if (e__ != cudaSuccess) return static_cast<int>(e__); \
+  } while (0)
+
+}  // namespace dfgan
