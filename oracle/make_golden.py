@@ -53,6 +53,9 @@ def ref_modules(g_sd, d_sd, depth):
         G.conv_out[1] = nn.Conv2d(plan[-1][2], 3, 3, 1, 1)
         dplan = O.discriminator_plan(n_c, depth)
         D.img_forward = nn.Sequential(D.img_forward[0], *[ResidualBlockD(a, b) for (_, a, b) in dplan])
+    dt = g_sd["linear_in.weight"].dtype
+    G.to(dt)
+    D.to(dt)
     G.load_state_dict(g_sd, strict=True)
     D.load_state_dict(d_sd, strict=True)
     assert list(G.state_dict().keys()) == list(g_sd.keys()), "generator key order differs from App. A"
@@ -135,8 +138,6 @@ def make(name):
     size = 4 * 2 ** depth
     images, sent, noise = O.synthetic_batch(batch, size, dtype=dt)
     G, D = ref_modules(g_sd, d_sd, depth)
-    G.to(dt)
-    D.to(dt)
     out = {}
     # forward activations through hooks on the reference modules
     hooks = []
