@@ -38,6 +38,9 @@ class ConvDesc(C.Structure):
         ("add_sw", C.c_int64), ("add_sh", C.c_int64), ("add_sn", C.c_int64),
         ("add_shift", C.c_int32), ("add_scale", C.c_float),
         ("mask_src", C.c_void_p), ("n_tile_hint", C.c_int32), ("max_ctas", C.c_int32),
+        ("out2", C.c_void_p), ("post_mode", C.c_int32),
+        ("tab_ga", C.c_void_p), ("tab_ba", C.c_void_p), ("tab_gb", C.c_void_p), ("tab_bb", C.c_void_p),
+        ("tab_stride", C.c_int64), ("out_nchw", C.c_void_p), ("co_valid", C.c_int32), ("tanh_out", C.c_int32),
     ]
 
 
@@ -48,6 +51,7 @@ class WgradDesc(C.Structure):
         ("g", View4), ("Cin", C.c_int32), ("Cout", C.c_int32),
         ("dw", C.c_void_p), ("s_co", C.c_int64), ("s_ci", C.c_int64), ("s_tap", C.c_int64),
         ("scale_dev", C.c_void_p), ("scale_imm", C.c_float), ("k_splits", C.c_int32),
+        ("ci_valid", C.c_int32), ("co_valid", C.c_int32),
     ]
 
 

@@ -4,13 +4,42 @@ from __future__ import annotations
 
 import ctypes as C
 
+P, I, L, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+
+class LinearItem(C.Structure):
+    _fields_ = [("inp", P), ("in_stride", L), ("w", P), ("bias", P), ("out", P), ("out_stride", L),
+                ("mask", P), ("k", C.c_int32), ("n_out", C.c_int32), ("o0", C.c_int32), ("relu", C.c_int32)]
+
 
 def declare(l: C.CDLL) -> None:
-    for name, (argtypes, restype) in _TABLE.items():
-        if hasattr(l, name):
-            fn = getattr(l, name)
-            fn.argtypes = argtypes
-            fn.restype = restype
+    for name, argtypes in _TABLE.items():
+        fn = getattr(l, name)   # AttributeError = header and library disagree: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
 
 
-_TABLE: dict = {}
+_TABLE: dict = {
+    "dfgan_affine2_fwd": [P, P, P, P, P, P, L, I, I, I, P],
+    "dfgan_affine2_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, L, P, P, P, I, I, I, P],
+    "dfgan_pool": [P, P, P, P, F, I, I, I, I, I, F, P],
+    "dfgan_dres_bwd": [P, P, P, P, P, P, I, I, I, P],
+    "dfgan_dot": [P, P, L, P, F, P],
+    "dfgan_im2col3": [P, P, P, I, I, I, P],
+    "dfgan_tanh_bwd_pack": [P, P, P, P, I, I, P],
+    "dfgan_nchw_to_nhwc": [P, P, I, I, I, P],
+    "dfgan_nhwc_to_nchw": [P, P, I, I, I, I, P],
+    "dfgan_rowsq": [P, I, L, P, P],
+    "dfgan_head_cat": [P, P, P, P, I, I, I, P],
+    "dfgan_head_cat_bwd": [P, P, P, I, I, I, P],
+    "dfgan_head_out": [P, P, P, I, I, P],
+    "dfgan_head_out_bwd": [P, P, P, P, P, P, I, I, P],
+    "dfgan_linear_batched": [P, I, I, I, I, I, P],
+    "dfgan_pack_weights": [P, P, I, I, I, I, I, I, I, P, F, P],
+    "dfgan_unfold_subpixel_wgrad": [P, P, I, I, P],
+    "dfgan_sqnorm": [P, L, P, P],
+    "dfgan_adam_step": [P, P, P, P, L, P, P, F, F, F, F, F, F, P],
+}
+
+EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
+           *_TABLE.keys()]

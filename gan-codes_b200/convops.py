@@ -78,15 +78,18 @@ def taps_4x4s2_dgrad(rows: int, a: int, c: int) -> list:
 
 # ------------------------------------------------------------------------------------ conv
 def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.Tensor, cout: int,
-             out: torch.Tensor, *, grid: Optional[tuple] = None, bias: Optional[torch.Tensor] = None,
-             scale_dev: Optional[torch.Tensor] = None, scale_imm: float = 1.0, lrelu_pre: bool = False,
-             aux: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None,
-             add_shift: int = 0, add_scale: float = 1.0, mask_src: Optional[torch.Tensor] = None,
-             n_tile: int = 0, max_ctas: int = 0) -> None:
-    """out = epilogue(sum_taps src[tap] (*) wpack[tap rows]) -- see dfgan_conv_run in the header.
+             out: Optional[torch.Tensor] = None, *, grid: Optional[tuple] = None,
+             bias: Optional[torch.Tensor] = None, scale_dev: Optional[torch.Tensor] = None,
+             scale_imm: float = 1.0, lrelu_pre: bool = False, aux: Optional[torch.Tensor] = None,
+             addend: Optional[torch.Tensor] = None, add_shift: int = 0, add_scale: float = 1.0,
+             mask_src: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, post_mode: int = 0,
+             tables: Optional[tuple] = None, tab_stride: int = 0, out_nchw: Optional[torch.Tensor] = None,
+             co_valid: int = 0, tanh_out: bool = False, n_tile: int = 0, max_ctas: int = 0) -> None:
+    """epilogue(sum_taps src[tap] (*) wpack[tap rows]) -- see dfgan_conv_run in include/dfgan_b200.h.
 
-    ``out`` may be a strided NHWC view (phase-interleaved writes); ``aux`` / ``mask_src`` must have
-    the same strides as ``out``.  ``grid`` = (N, H, W) of the output grid (default: out.shape[:3]).
+    ``out`` / ``aux`` / ``out2`` / ``mask_src`` are NHWC bf16 tensors (possibly strided phase views) that
+    must share one set of strides.  ``grid`` = (N, H, W) of the output grid (default: shape of the first
+    given output).  ``tables`` = (ga, ba, gb, bb) fp32 views [N, C] with row stride ``tab_stride``.
     """
     d = ConvDesc()
     assert 1 <= len(srcs) <= _lib.MAX_SRC and 1 <= len(taps) <= _lib.MAX_TAPS
@@ -97,30 +100,44 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
         d.taps[i] = Tap(si, dy, dx, wrow)
     assert wpack.dtype == torch.bfloat16 and wpack.is_contiguous() and wpack.dim() == 2
     d.wpack, d.w_rows, d.Cin, d.Cout = wpack.data_ptr(), wpack.shape[0], wpack.shape[1], cout
-    n, h, w = grid if grid is not None else out.shape[:3]
+    ref = next((t for t in (out, aux, out2) if t is not None), None)
+    if ref is not None:
+        assert ref.dtype == torch.bfloat16 and ref.stride(3) == 1 and ref.shape[3] == cout
+        d.out_sn, d.out_sh, d.out_sw = ref.stride(0), ref.stride(1), ref.stride(2)
+        for t in (out, aux, out2, mask_src):
+            if t is not None:
+                assert t.dtype == torch.bfloat16 and t.stride() == ref.stride(), (t.stride(), ref.stride())
+    else:
+        assert out_nchw is not None and mask_src is None
+    n, h, w = grid if grid is not None else (ref.shape[:3] if ref is not None else
+                                              (out_nchw.shape[0], out_nchw.shape[2], out_nchw.shape[3]))
     d.N, d.H, d.W = n, h, w
-    assert out.dtype == torch.bfloat16 and out.stride(3) == 1 and out.shape[3] == cout
-    d.out, d.out_sn, d.out_sh, d.out_sw = out.data_ptr(), out.stride(0), out.stride(1), out.stride(2)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == cout
+    d.out, d.aux, d.out2, d.mask_src = _ptr(out), _ptr(aux), _ptr(out2), _ptr(mask_src)
     d.bias, d.scale_dev, d.scale_imm = _ptr(bias), _ptr(scale_dev), scale_imm
     d.lrelu_pre, d.slope = int(lrelu_pre), SLOPE
-    for t in (aux, mask_src):
-        if t is not None:
-            assert t.dtype == torch.bfloat16 and t.stride() == out.stride(), (t.stride(), out.stride())
-    d.aux, d.mask_src = _ptr(aux), _ptr(mask_src)
     if addend is not None:
         assert addend.dtype == torch.bfloat16 and addend.stride(3) == 1 and addend.shape[3] == cout
         d.addend = addend.data_ptr()
         d.add_sn, d.add_sh, d.add_sw = addend.stride(0), addend.stride(1), addend.stride(2)
     d.add_shift, d.add_scale = add_shift, add_scale
+    d.post_mode = post_mode
+    if post_mode == 2:
+        assert tables is not None and all(t.dtype == torch.float32 and t.stride(-1) == 1 for t in tables)
+        d.tab_ga, d.tab_ba, d.tab_gb, d.tab_bb = (t.data_ptr() for t in tables)
+        d.tab_stride = tab_stride
+    if out_nchw is not None:
+        assert out_nchw.dtype == torch.float32 and out_nchw.is_contiguous()
+        assert tuple(out_nchw.shape) == (n, co_valid, h, w), (out_nchw.shape, (n, co_valid, h, w))
+        d.out_nchw, d.co_valid, d.tanh_out = out_nchw.data_ptr(), co_valid, int(tanh_out)
     d.n_tile_hint, d.max_ctas = n_tile, max_ctas
     _lib.check(_lib.lib().dfgan_conv_run(C.byref(d), _stream()), "dfgan_conv_run")
 
 
 def wgrad_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], g: torch.Tensor, dw: torch.Tensor,
               strides: tuple, *, scale_dev: Optional[torch.Tensor] = None, scale_imm: float = 1.0,
-              k_splits: int = 0) -> None:
+              k_splits: int = 0, ci_valid: int = 0, co_valid: int = 0) -> None:
     """dw[co, ci, tap] += scale * sum_pixels g[p, co] * src[tap][p + shift, ci]  (fp32 atomics).
 
     ``taps`` entries are (src, dy, dx, tap_id); ``strides`` = element strides (s_co, s_ci, s_tap) of dw.
@@ -137,17 +154,47 @@ def wgrad_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], g: torch.Tens
     d.dw = dw.data_ptr()
     d.s_co, d.s_ci, d.s_tap = strides
     d.scale_dev, d.scale_imm, d.k_splits = _ptr(scale_dev), scale_imm, k_splits
+    d.ci_valid, d.co_valid = ci_valid, co_valid
     _lib.check(_lib.lib().dfgan_wgrad_run(C.byref(d), _stream()), "dfgan_wgrad_run")
 
 
-# ------------------------------------------------------------------------------------ packing (torch)
-def pack_fwd(w: torch.Tensor) -> torch.Tensor:
-    """OIHW fp32 -> bf16 [kh*kw*Cout, Cin] (row = tap*Cout + co): B operand of the forward GEMM."""
-    co, ci, kh, kw = w.shape
-    return w.permute(2, 3, 0, 1).reshape(kh * kw * co, ci).to(torch.bfloat16).contiguous()
+# ------------------------------------------------------------------------------------ sub-pixel taps
+# nearest-2x upsample followed by conv3x3/pad1 == four phase-specific 2x2 convolutions on the low-res
+# input.  Output row 2i+a reads low-res rows i+dy with the 3x3 rows folded as below.
+SUBPIX_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}   # phase -> ((dy, rows summed), ..)
 
 
-def pack_dgrad(w: torch.Tensor) -> torch.Tensor:
-    """OIHW fp32 -> bf16 [kh*kw*Cin, Cout] (row = tap*Cin + ci): B operand of the data-gradient GEMM."""
-    co, ci, kh, kw = w.shape
-    return w.permute(2, 3, 1, 0).reshape(kh * kw * ci, co).to(torch.bfloat16).contiguous()
+def subpixel_slots() -> list:
+    """16 slots (phase a, phase c, dy index, dx index) -> list of source taps r*3+s summed into the slot."""
+    slots = []
+    for a in (0, 1):
+        for c in (0, 1):
+            for (_, rs) in SUBPIX_ROWS[a]:
+                for (_, ss) in SUBPIX_ROWS[c]:
+                    slots.append([r * 3 + s for r in rs for s in ss])
+    return slots
+
+
+def taps_subpixel_fwd(rows: int, a: int, c: int) -> list:
+    base = (a * 2 + c) * 4
+    return [(0, dy, dx, (base + yi * 2 + xi) * rows)
+            for yi, (dy, _) in enumerate(SUBPIX_ROWS[a]) for xi, (dx, _) in enumerate(SUBPIX_ROWS[c])]
+
+
+def taps_subpixel_dgrad(rows: int) -> list:
+    """Data gradient wrt the low-res input: sources are the four phase views (index a*2+c) of the hi-res
+    gradient, pixel (i,j) receives g_phase[i-dy, j-dx] * W_slot^T."""
+    out = []
+    for a in (0, 1):
+        for c in (0, 1):
+            base = (a * 2 + c) * 4
+            for yi, (dy, _) in enumerate(SUBPIX_ROWS[a]):
+                for xi, (dx, _) in enumerate(SUBPIX_ROWS[c]):
+                    out.append((a * 2 + c, -dy, -dx, (base + yi * 2 + xi) * rows))
+    return out
+
+
+def taps_subpixel_wgrad(a: int, c: int) -> list:
+    base = (a * 2 + c) * 4
+    return [(0, dy, dx, base + yi * 2 + xi)
+            for yi, (dy, _) in enumerate(SUBPIX_ROWS[a]) for xi, (dx, _) in enumerate(SUBPIX_ROWS[c])]

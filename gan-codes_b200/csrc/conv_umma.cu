@@ -46,6 +46,12 @@ struct ConvK {
   int add_shift;
   float add_scale;
   const __nv_bfloat16* mask_src;
+  __nv_bfloat16* out2;
+  int post_mode;  // 0 none, 1 lrelu, 2 affine-lrelu-affine-lrelu
+  const float *tab_ga, *tab_ba, *tab_gb, *tab_bb;
+  long long tab_stride;
+  float* out_nchw;  // fp32 [N][co_valid][H][W] store (image boundary), optional tanh
+  int co_valid, tanh_out;
 };
 
 __device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -65,6 +71,27 @@ struct PipeState {
     }
   }
 };
+
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v) {
+  uint4 s0, s1;
+  s0.x = pack_bf16x2(v[0], v[1]), s0.y = pack_bf16x2(v[2], v[3]);
+  s0.z = pack_bf16x2(v[4], v[5]), s0.w = pack_bf16x2(v[6], v[7]);
+  s1.x = pack_bf16x2(v[8], v[9]), s1.y = pack_bf16x2(v[10], v[11]);
+  s1.z = pack_bf16x2(v[12], v[13]), s1.w = pack_bf16x2(v[14], v[15]);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = s0;
+  d[1] = s1;
+}
+__device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* src, float* v) {
+  const uint4* sp = reinterpret_cast<const uint4*>(src);
+  const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+  const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) unpack_bf16x2(u[i], v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ float round_bf16(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
 
 template <int BK>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -205,50 +232,49 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
           }
-          if (p.aux) {
-            uint4 s0, s1;
-            s0.x = pack_bf16x2(v[0], v[1]), s0.y = pack_bf16x2(v[2], v[3]);
-            s0.z = pack_bf16x2(v[4], v[5]), s0.w = pack_bf16x2(v[6], v[7]);
-            s1.x = pack_bf16x2(v[8], v[9]), s1.y = pack_bf16x2(v[10], v[11]);
-            s1.z = pack_bf16x2(v[12], v[13]), s1.w = pack_bf16x2(v[14], v[15]);
-            uint4* dst = reinterpret_cast<uint4*>(p.aux + o_off + col);
-            dst[0] = s0;
-            dst[1] = s1;
+          if (p.mask_src) {
+            float m[16];
+            load_bf16x16(p.mask_src + o_off + col, m);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : p.slope);
           }
+          if (p.aux) store_bf16x16(p.aux + o_off + col, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= scale;
           if (p.addend) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.addend + a_off + col);
-            const uint4 s0 = __ldg(src), s1 = __ldg(src + 1);
-            const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float a[16];
+            load_bf16x16(p.addend + a_off + col, a);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a, b;
-              unpack_bf16x2(u[i], a, b);
-              v[2 * i] += p.add_scale * a;
-              v[2 * i + 1] += p.add_scale * b;
+            for (int i = 0; i < 16; ++i) v[i] += p.add_scale * a[i];
+          }
+          if (p.out_nchw) {
+            // image boundary: fp32 planar store, lanes of a warp hold consecutive w -> coalesced
+            const long long hw = static_cast<long long>(p.H) * p.W;
+            float* dst = p.out_nchw + (static_cast<long long>(n) * p.co_valid) * hw +
+                         static_cast<long long>(h) * p.W + w;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (col + i < p.co_valid) dst[(col + i) * hw] = p.tanh_out ? tanhf(v[i]) : v[i];
             }
           }
-          if (p.mask_src) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.mask_src + o_off + col);
-            const uint4 s0 = __ldg(src), s1 = __ldg(src + 1);
-            const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          if (p.out) store_bf16x16(p.out + o_off + col, v);
+          if (p.post_mode) {
+            // the follow-up pointwise chain is evaluated on the bf16-rounded value that `out`/`aux`
+            // hold, so a backward pass that recomputes it from the stored tensor sees identical masks
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a, b;
-              unpack_bf16x2(u[i], a, b);
-              v[2 * i] *= (a > 0.f ? 1.f : p.slope);
-              v[2 * i + 1] *= (b > 0.f ? 1.f : p.slope);
+            for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+            if (p.post_mode == 2) {
+              const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float u = lrelu(fmaf(__ldg(p.tab_ga + t_off + i), v[i], __ldg(p.tab_ba + t_off + i)), p.slope);
+                v[i] = fmaf(__ldg(p.tab_gb + t_off + i), u, __ldg(p.tab_bb + t_off + i));
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+            store_bf16x16(p.out2 + o_off + col, v);
           }
-          uint4 s0, s1;
-          s0.x = pack_bf16x2(v[0], v[1]), s0.y = pack_bf16x2(v[2], v[3]);
-          s0.z = pack_bf16x2(v[4], v[5]), s0.w = pack_bf16x2(v[6], v[7]);
-          s1.x = pack_bf16x2(v[8], v[9]), s1.y = pack_bf16x2(v[10], v[11]);
-          s1.z = pack_bf16x2(v[12], v[13]), s1.w = pack_bf16x2(v[14], v[15]);
-          uint4* dst = reinterpret_cast<uint4*>(p.out + o_off + col);
-          dst[0] = s0;
-          dst[1] = s1;
         }
       }
       tc_fence_before();
@@ -293,6 +319,7 @@ struct WgradK {
   long long s_co, s_ci, s_tap;
   const float* scale_dev;
   float scale_imm;
+  int ci_valid, co_valid;
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -419,9 +446,9 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const int nt = r % p.n_tiles_n;
       const int mt = r / p.n_tiles_n;
       const int rb = mt * blocks_per_tile + (row >> p.lcb);
-      const bool valid = rb < p.row_blocks;
-      const int t = valid ? rb / p.blocks_per_tap : 0;
       const int ci = ((rb % p.blocks_per_tap) << p.lcb) + (row & (p.cb - 1));
+      const bool valid = rb < p.row_blocks && ci < p.ci_valid;
+      const int t = rb < p.row_blocks ? rb / p.blocks_per_tap : 0;
       float* dst = p.dw + ci * p.s_ci + p.tap_id[t] * p.s_tap;
       wait_bounded(&tfull[as], aphase);
       tc_fence_after();
@@ -433,7 +460,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const int col = nt * p.n_tile + c;
         if (valid && col < p.Cout) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dst + (col + i) * p.s_co, v[i] * scale);
+          for (int i = 0; i < 16; ++i)
+            if (col + i < p.co_valid) atomicAdd(dst + (col + i) * p.s_co, v[i] * scale);
         }
       }
       tc_fence_before();
@@ -472,7 +500,11 @@ using namespace dfgan;
 
 extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!d || !d->out || !d->wpack) return DFGAN_E_ARG;
+  if (!d || !d->wpack) return DFGAN_E_ARG;
+  if (!d->out && !d->aux && !d->out2 && !d->out_nchw) return DFGAN_E_ARG;
+  if (d->post_mode < 0 || d->post_mode > 2 || (d->post_mode && !d->out2)) return DFGAN_E_ARG;
+  if (d->post_mode == 2 && !(d->tab_ga && d->tab_ba && d->tab_gb && d->tab_bb)) return DFGAN_E_ARG;
+  if (d->out_nchw && (d->co_valid < 1 || d->co_valid > d->Cout)) return DFGAN_E_ARG;
   if (d->n_src < 1 || d->n_src > DFGAN_MAX_SRC || d->n_taps < 1 || d->n_taps > DFGAN_MAX_TAPS)
     return DFGAN_E_ARG;
   if (d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1) return DFGAN_E_SHAPE;
@@ -517,6 +549,11 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   k.add_sw = d->add_sw, k.add_sh = d->add_sh, k.add_sn = d->add_sn;
   k.add_shift = d->add_shift, k.add_scale = d->add_scale;
   k.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
+  k.out2 = static_cast<__nv_bfloat16*>(d->out2);
+  k.post_mode = d->post_mode;
+  k.tab_ga = d->tab_ga, k.tab_ba = d->tab_ba, k.tab_gb = d->tab_gb, k.tab_bb = d->tab_bb;
+  k.tab_stride = d->tab_stride;
+  k.out_nchw = d->out_nchw, k.co_valid = d->co_valid, k.tanh_out = d->tanh_out;
 
   for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
     const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
@@ -610,6 +647,8 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   k.dw = d->dw;
   k.s_co = d->s_co, k.s_ci = d->s_ci, k.s_tap = d->s_tap;
   k.scale_dev = d->scale_dev, k.scale_imm = d->scale_imm;
+  k.ci_valid = d->ci_valid > 0 ? d->ci_valid : d->Cin;
+  k.co_valid = d->co_valid > 0 ? d->co_valid : d->Cout;
 
   for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
     const dfgan_view4& v = d->src[s < d->n_src ? s : 0];

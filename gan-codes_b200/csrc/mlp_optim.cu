@@ -1,0 +1,288 @@
+// (1) The 56 gamma/beta MLPs of the generator's AffineBlocks (generator/fusion_block.py:8-18,34-35) and
+//     linear_in (generator/model.py:13,34) as ONE batched launch per layer over a device-side work table,
+//     forward and backward.  These are weight-bandwidth-bound GEMV-like problems (batch 32..256 rows against
+//     6.5 M fp32 parameters): fp32 CUDA-core math straight from the master weights, no packing.
+// (2) Weight packing fp32 OIHW -> bf16 GEMM operands (incl. the sub-pixel folding of upsample->conv3x3 and
+//     the un-folding of its weight gradient).
+// (3) Fused global-norm clip + Adam over flat parameter buffers (deep_fusion_gan/model.py:42-43,195-197).
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace dfgan {
+
+constexpr int kLinThreads = 256;
+constexpr int kLinBT = 32;  // batch rows per block tile
+
+// out[b, o] = act(sum_i in[b, i] * w[o, i] + bias[o]),  o in [o0, o0 + 64)
+__global__ void __launch_bounds__(kLinThreads)
+    linear_fwd_kernel(const dfgan_linear_item* __restrict__ items, int B) {
+  extern __shared__ float sm[];
+  const dfgan_linear_item it = items[blockIdx.x];
+  const int b0 = blockIdx.y * kLinBT;
+  const int K = it.k;
+  const int ld = K + 1;
+  for (int i = threadIdx.x; i < kLinBT * K; i += kLinThreads) {
+    const int b = i / K, k = i - b * K;
+    sm[b * ld + k] = (b0 + b < B) ? __ldg(it.in + static_cast<long long>(b0 + b) * it.in_stride + k) : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xrow = sm + lane * ld;
+  for (int o = warp; o < 64; o += kLinThreads / 32) {
+    const int oo = it.o0 + o;
+    if (oo >= it.n_out) break;
+    const float* wrow = it.w + static_cast<long long>(oo) * K;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) acc = fmaf(xrow[k], __ldg(wrow + k), acc);
+    acc += it.bias ? __ldg(it.bias + oo) : 0.f;
+    if (it.relu) acc = fmaxf(acc, 0.f);
+    if (b0 + lane < B) it.out[static_cast<long long>(b0 + lane) * it.out_stride + oo] = acc;
+  }
+}
+
+// din[b, k] (+)= mask(b,k) * sum_o dout[b, o] * w[o, k];  k tile = 64 columns per item (o0 reused as k0)
+__global__ void __launch_bounds__(kLinThreads)
+    linear_bwd_data_kernel(const dfgan_linear_item* __restrict__ items, int B) {
+  extern __shared__ float sm[];
+  const dfgan_linear_item it = items[blockIdx.x];
+  const int b0 = blockIdx.y * kLinBT;
+  const int NO = it.n_out;
+  // stage dout tile [32][NO]
+  for (int i = threadIdx.x; i < kLinBT * NO; i += kLinThreads) {
+    const int b = i / NO, o = i - b * NO;
+    sm[b * NO + o] = (b0 + b < B) ? __ldg(it.out + static_cast<long long>(b0 + b) * it.out_stride + o) : 0.f;
+  }
+  __syncthreads();
+  // thread -> (k = o0 + tid % 64, batch group = tid / 64 -> 8 rows)
+  const int k = it.o0 + (threadIdx.x & 63);
+  const int bg = threadIdx.x >> 6;
+  if (k >= it.k) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int o = 0; o < NO; ++o) {
+    const float w = __ldg(it.w + static_cast<long long>(o) * it.k + k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(sm[(bg * 8 + j) * NO + o], w, acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = b0 + bg * 8 + j;
+    if (b < B) {
+      const long long off = static_cast<long long>(b) * it.in_stride + k;
+      // relu backward: `mask` holds the forward activation (same layout as din)
+      const_cast<float*>(it.in)[off] = (it.mask && !(__ldg(it.mask + off) > 0.f)) ? 0.f : acc[j];
+    }
+  }
+}
+
+// dw[o, k] += sum_b dout[b, o] * in[b, k] ; dbias[o] += sum_b dout[b, o];  64 outputs per item
+__global__ void __launch_bounds__(kLinThreads)
+    linear_bwd_weight_kernel(const dfgan_linear_item* __restrict__ items, int B) {
+  extern __shared__ float sm[];  // dout tile [B chunk 32][64] + in tile [32][K]
+  const dfgan_linear_item it = items[blockIdx.x];
+  const int K = it.k;
+  float* s_d = sm;
+  float* s_x = sm + kLinBT * 64;
+  // thread -> column k = tid % K_pad ... each thread owns (o subset) x (k): loop layout below
+  const int n_o = min(64, it.n_out - it.o0);
+  for (int b0 = 0; b0 < B; b0 += kLinBT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kLinBT * 64; i += kLinThreads) {
+      const int b = i >> 6, o = i & 63;
+      s_d[i] = (b0 + b < B && o < n_o)
+                   ? __ldg(it.out + static_cast<long long>(b0 + b) * it.out_stride + it.o0 + o)
+                   : 0.f;
+    }
+    for (int i = threadIdx.x; i < kLinBT * K; i += kLinThreads) {
+      const int b = i / K, k = i - b * K;
+      s_x[i] = (b0 + b < B) ? __ldg(it.in + static_cast<long long>(b0 + b) * it.in_stride + k) : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_o * K; e += kLinThreads) {
+      const int o = e / K, k = e - o * K;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int b = 0; b < kLinBT; ++b) acc = fmaf(s_d[b * 64 + o], s_x[b * K + k], acc);
+      float* dst = const_cast<float*>(it.w) + static_cast<long long>(it.o0 + o) * K + k;
+      *dst += acc;  // each (o,k) is owned by exactly one thread of one block
+    }
+    if (it.bias && threadIdx.x < n_o) {
+      float acc = 0.f;
+      for (int b = 0; b < kLinBT; ++b) acc += s_d[b * 64 + threadIdx.x];
+      const_cast<float*>(it.bias)[it.o0 + threadIdx.x] += acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ weight packing
+struct PackP {
+  const float* w;  // [Co][Ci][kh*kw] fp32
+  __nv_bfloat16* out;
+  int Co, Ci, KK;
+  int transpose;  // 0: rows = co, cols = ci ; 1: rows = ci, cols = co
+  int rows_pad, cols_pad, n_slots;
+  float scale;
+  int8_t taps[16][4];  // per slot: source tap indices summed (-1 = unused)
+};
+__global__ void pack_kernel(const __grid_constant__ PackP p) {
+  const long long total = static_cast<long long>(p.n_slots) * p.rows_pad * p.cols_pad;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int col = i % p.cols_pad;
+  const long long t = i / p.cols_pad;
+  const int row = t % p.rows_pad;
+  const int slot = t / p.rows_pad;
+  const int co = p.transpose ? col : row, ci = p.transpose ? row : col;
+  float v = 0.f;
+  if (co < p.Co && ci < p.Ci) {
+    const float* src = p.w + (static_cast<long long>(co) * p.Ci + ci) * p.KK;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (p.taps[slot][j] >= 0) v += __ldg(src + p.taps[slot][j]);
+  }
+  p.out[i] = __float2bfloat16_rn(v * p.scale);
+}
+// dw[co][ci][r*3+s] += sum_{a,c} folded[(a*2+c)*4 + dyi_a(r)*2 + dxi_c(s)][co][ci]   (sub-pixel un-fold)
+__global__ void unfold_kernel(const float* __restrict__ folded, float* __restrict__ dw, int Co, int Ci) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(Co) * Ci * 9;
+  if (i >= total) return;
+  const int t = i % 9;
+  const long long cc = i / 9;  // co*Ci + ci
+  const int r = t / 3, s = t % 3;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int yi = a == 0 ? (r == 0 ? 0 : 1) : (r == 2 ? 1 : 0);
+      const int xi = c == 0 ? (s == 0 ? 0 : 1) : (s == 2 ? 1 : 0);
+      acc += __ldg(folded + static_cast<long long>((a * 2 + c) * 4 + yi * 2 + xi) * Co * Ci + cc);
+    }
+  dw[i] += acc;
+}
+
+// ------------------------------------------------------------------------------------ clip + Adam
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* out) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 4; i < n; i += gridDim.x * 1024LL) {
+    if (i + 3 < n) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g + i));
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (long long j = i; j < n; ++j) acc += g[j] * g[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(out, s);
+  }
+}
+// torch.nn.utils.clip_grad_norm_(max_norm) followed by torch.optim.Adam.step():
+//   g' = g * gscale * min(1, max_norm / (gscale*sqrt(sumsq) + 1e-6))
+//   m = b1 m + (1-b1) g' ; v = b2 v + (1-b2) g'^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256)
+    adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, long long n, const float* sumsq, const int* step, float gscale,
+                float max_norm, float lr, float b1, float b2, float eps) {
+  const float t = static_cast<float>(*step);
+  const float norm = gscale * sqrtf(__ldg(sumsq));
+  const float coef = gscale * (max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f);
+  const float c1 = 1.f - powf(b1, t), c2s = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / c1;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) / c2s + eps);
+  }
+}
+
+}  // namespace dfgan
+
+using namespace dfgan;
+#define STREAM(s) static_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int dfgan_linear_batched(const dfgan_linear_item* items_dev, int n_items, int B, int k_max, int n_out_max,
+                         int mode, dfgan_stream_t st) {
+  if (!items_dev || n_items < 1 || B < 1 || k_max < 1 || k_max > 256) return DFGAN_E_ARG;
+  const int by = (B + kLinBT - 1) / kLinBT;
+  if (mode == 0) {
+    const size_t smem = static_cast<size_t>(kLinBT) * (k_max + 1) * sizeof(float);
+    linear_fwd_kernel<<<dim3(n_items, by), kLinThreads, smem, STREAM(st)>>>(items_dev, B);
+  } else if (mode == 1) {
+    if (n_out_max < 1 || n_out_max > 256) return DFGAN_E_ARG;
+    const size_t smem = static_cast<size_t>(kLinBT) * n_out_max * sizeof(float);
+    linear_bwd_data_kernel<<<dim3(n_items, by), kLinThreads, smem, STREAM(st)>>>(items_dev, B);
+  } else if (mode == 2) {
+    const size_t smem = static_cast<size_t>(kLinBT) * (64 + k_max) * sizeof(float);
+    linear_bwd_weight_kernel<<<n_items, kLinThreads, smem, STREAM(st)>>>(items_dev, B);
+  } else {
+    return DFGAN_E_ARG;
+  }
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int transpose, int rows_pad,
+                       int cols_pad, int n_slots, const int8_t* slot_taps /* host [n_slots][4] */,
+                       float scale, dfgan_stream_t st) {
+  if (!w || !out || !slot_taps || n_slots < 1 || n_slots > 16) return DFGAN_E_ARG;
+  if (rows_pad < (transpose ? Ci : Co) || cols_pad < (transpose ? Co : Ci)) return DFGAN_E_SHAPE;
+  PackP p{};
+  p.w = w, p.out = static_cast<__nv_bfloat16*>(out);
+  p.Co = Co, p.Ci = Ci, p.KK = KK, p.transpose = transpose;
+  p.rows_pad = rows_pad, p.cols_pad = cols_pad, p.n_slots = n_slots, p.scale = scale;
+  for (int s = 0; s < 16; ++s)
+    for (int j = 0; j < 4; ++j) p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
+  const long long total = static_cast<long long>(n_slots) * rows_pad * cols_pad;
+  pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, STREAM(st)>>>(p);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_unfold_subpixel_wgrad(const float* folded, float* dw, int Co, int Ci, dfgan_stream_t st) {
+  if (!folded || !dw) return DFGAN_E_ARG;
+  const long long total = static_cast<long long>(Co) * Ci * 9;
+  unfold_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, STREAM(st)>>>(folded, dw, Co, Ci);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_sqnorm(const float* g, int64_t n, float* out, dfgan_stream_t st) {
+  if (!g || !out || n < 1 || (reinterpret_cast<uintptr_t>(g) & 15)) return DFGAN_E_ARG;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+  sqnorm_kernel<<<static_cast<int>(blocks), 256, 0, STREAM(st)>>>(g, n, out);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                    const int* step, float gscale, float max_norm, float lr, float b1, float b2, float eps,
+                    dfgan_stream_t st) {
+  if (!p || !g || !m || !v || !sumsq || !step || n < 1) return DFGAN_E_ARG;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  adam_kernel<<<static_cast<int>(blocks), 256, 0, STREAM(st)>>>(p, g, m, v, n, sumsq, step, gscale, max_norm,
+                                                               lr, b1, b2, eps);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+}  // extern "C"

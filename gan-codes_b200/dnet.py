@@ -1,0 +1,288 @@
+"""Kernel programs of the discriminator: trunk (`build_embeds`), logit head (`get_logits`), their first-order
+backward and the tangent-forward sweep that implements the MA-GP double backward.
+
+Reference arithmetic (Deep_Fusion_GAN/src/): discriminator/model.py:11-59, discriminator/residual_block.py:7-30,
+deep_fusion_gan/model.py:59-85 (autograd.grad with create_graph) and :207 (its backward).
+
+Everything here only sequences C-ABI kernel launches on the current stream; tensors are NHWC bf16 between
+kernels, fp32 NCHW at the API boundary (images, embeds) and fp32 for parameters / gradients.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import convops as co
+from . import kernels as K
+
+BF16, F32 = torch.bfloat16, torch.float32
+SENT_DIM = 256
+
+
+def d_plan(params: Dict[str, torch.Tensor]) -> List[tuple]:
+    """(prefix, C_in, C_out, has_scale_conv) per ResidualBlockD, read off the parameter shapes."""
+    plan, k = [], 1
+    while f"img_forward.{k}.gamma" in params:
+        w = params[f"img_forward.{k}.residual_conv.0.weight"]
+        plan.append((f"img_forward.{k}", w.shape[1], w.shape[0], f"img_forward.{k}.scale_conv.weight" in params))
+        k += 1
+    return plan
+
+
+TAPS3_ID = [(0, r - 1, s - 1, r * 3 + s) for r in range(3) for s in range(3)]
+TAPS4_ID = [(src, dy, dx, i) for i, (src, dy, dx, _) in enumerate(co.taps_4x4s2(0))]
+TAPS_POOL = [(i, 0, 0, 0) for i in range(4)]
+
+
+class DPacked:
+    """bf16 GEMM operands of one discriminator parameter set; `refresh` re-packs after an optimiser step."""
+
+    def __init__(self, params: Dict[str, torch.Tensor]):
+        self.plan = d_plan(params)
+        dev = params["img_forward.0.weight"].device
+        self.n_c = params["img_forward.0.weight"].shape[0]
+        if self.n_c != 32:
+            raise ValueError("stem kernel is built for n_c == 32 (reference: Discriminator(n_c=32), "
+                             "deep_fusion_gan/model.py:29)")
+        e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
+        self.w0_f, self.w0_d = e(32, 32), e(9 * 16, 32)
+        self.blocks = []
+        for (_, cin, cout, sc) in self.plan:
+            self.blocks.append(dict(w4_f=e(16 * cout, cin), w4_d=e(16 * cin, cout), w3_f=e(9 * cout, cout),
+                                    w3_d=e(9 * cout, cout), ws_f=e(cout, cin) if sc else None,
+                                    ws_d=e(cin, cout) if sc else None))
+        wh = params["img_sentence_forward.0.weight"]
+        self.ch, self.ccat = wh.shape[0], wh.shape[1]
+        self.wh_f, self.wh_d = e(9 * self.ch, self.ccat), e(9 * self.ccat, self.ch)
+        self.refresh(params)
+
+    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
+        K.pack_weights(params["img_forward.0.weight"], self.w0_f, as_matrix=True, cols_pad=32)
+        K.pack_weights(params["img_forward.0.weight"], self.w0_d, transpose=True, rows_pad=16)
+        for (p, cin, cout, sc), b in zip(self.plan, self.blocks):
+            w4, w3 = params[p + ".residual_conv.0.weight"], params[p + ".residual_conv.2.weight"]
+            K.pack_weights(w4, b["w4_f"])
+            K.pack_weights(w4, b["w4_d"], transpose=True)
+            K.pack_weights(w3, b["w3_f"])
+            K.pack_weights(w3, b["w3_d"], transpose=True)
+            if sc:
+                K.pack_weights(params[p + ".scale_conv.weight"], b["ws_f"], scale=0.25)
+                K.pack_weights(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)
+        K.pack_weights(params["img_sentence_forward.0.weight"], self.wh_f)
+        K.pack_weights(params["img_sentence_forward.0.weight"], self.wh_d, transpose=True)
+
+
+def _oihw_strides(w: torch.Tensor) -> tuple:
+    co_, ci, kh, kw = w.shape
+    return (ci * kh * kw, kh * kw, 1)
+
+
+def _check_image(img: torch.Tensor, n_blocks: int) -> None:
+    if img.dim() != 4 or img.shape[1] != 3 or img.shape[2] != img.shape[3] or img.shape[2] != 4 << n_blocks:
+        # same failure the reference produces at the torch.cat of get_logits (discriminator/model.py:54)
+        raise RuntimeError(f"Sizes of tensors must match: image {tuple(img.shape)} does not reduce to a 4x4 "
+                           f"embed grid through {n_blocks} down-blocks")
+
+
+# ------------------------------------------------------------------------------------------------ trunk
+def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = None) -> torch.Tensor:
+    """discriminator/model.py:36-41.  img: fp32 NCHW [N,3,H,H] -> embeds NHWC bf16 [N,4,4,16*n_c].
+    ctx (optional dict) receives the activations the backward / tangent sweeps need."""
+    _check_image(img, len(pk.plan))
+    n, _, h, w = img.shape
+    dev = img.device
+    e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
+    xcol = e(n, h, w, 32)
+    K.im2col3(img, xcol)
+    x = e(n, h, w, pk.n_c)
+    co.conv_run([xcol], co.taps_1x1(), pk.w0_f, pk.n_c, x, bias=params["img_forward.0.bias"])
+    saved = []
+    for (p, cin, cout, sc), b in zip(pk.plan, pk.blocks):
+        h, w = h // 2, w // 2
+        pv = co.parity_views(x)
+        s = e(n, h, w, cout)
+        if sc:   # avg_pool2d(conv1x1(x)+b) == conv1x1(avg_pool2d(x))+b, pooling folded into 4 taps (App. C-2)
+            co.conv_run(pv, TAPS_POOL, b["ws_f"], cout, s, bias=params[p + ".scale_conv.bias"])
+        else:
+            K.pool(x, s, shift=1, scale=0.25)
+        c1 = e(n, h, w, cout)
+        co.conv_run(pv, co.taps_4x4s2(cout), b["w4_f"], cout, c1, lrelu_pre=True)
+        y, r = e(n, h, w, cout), e(n, h, w, cout)
+        co.conv_run([c1], co.taps_3x3(cout), b["w3_f"], cout, y, lrelu_pre=True, aux=r,
+                    scale_dev=params[p + ".gamma"], addend=s)
+        saved.append((x, c1, r))
+        x = y
+    if ctx is not None:
+        ctx.update(xcol=xcol, saved=saved, n=n)
+    return x
+
+
+def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: Optional[dict],
+                   need_gx: bool, cots: Optional[dict] = None) -> Optional[torch.Tensor]:
+    """First-order backward of the trunk.  g_emb: NHWC bf16 cotangent of the embeds.  grads: name -> fp32
+    accumulator (None = skip all parameter gradients, i.e. the G step / the first GP sweep).  cots (optional
+    dict) receives the cotangent at every conv output for the MA-GP second sweep.  Returns d/d(image) as fp32
+    NCHW when need_gx."""
+    dev = g_emb.device
+    n = ctx["n"]
+    e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
+    g_y = g_emb
+    kept = []
+    for (p, cin, cout, sc), b, (x, c1, r) in zip(reversed(pk.plan), reversed(pk.blocks), reversed(ctx["saved"])):
+        h, w = c1.shape[1], c1.shape[2]
+        g_c2 = e(n, h, w, cout)
+        K.dres_bwd(g_y, r, g_c2, params[p + ".gamma"],
+                   dgamma=grads[p + ".gamma"] if grads is not None else None,
+                   colsum=grads[p + ".scale_conv.bias"] if (grads is not None and sc) else None)
+        g_c1 = e(n, h, w, cout)
+        co.conv_run([g_c2], co.taps_3x3_dgrad(cout), b["w3_d"], cout, g_c1, mask_src=c1)
+        if sc:
+            g_s = e(n, h, w, cin)
+            co.conv_run([g_y], co.taps_1x1(), b["ws_d"], cin, g_s)
+        else:
+            g_s = g_y
+        g_x = e(n, 2 * h, 2 * w, cin)
+        for a in (0, 1):
+            for c in (0, 1):
+                co.conv_run([g_c1], co.taps_4x4s2_dgrad(cin, a, c), b["w4_d"], cin, g_x[:, a::2, c::2, :],
+                            addend=g_s, add_scale=0.25)
+        if grads is not None:
+            w3, w4 = params[p + ".residual_conv.2.weight"], params[p + ".residual_conv.0.weight"]
+            co.wgrad_run([c1], TAPS3_ID, g_c2, grads[p + ".residual_conv.2.weight"], _oihw_strides(w3))
+            pv = co.parity_views(x)
+            co.wgrad_run(pv, TAPS4_ID, g_c1, grads[p + ".residual_conv.0.weight"], _oihw_strides(w4))
+            if sc:
+                ws = params[p + ".scale_conv.weight"]
+                co.wgrad_run(pv, TAPS_POOL, g_y, grads[p + ".scale_conv.weight"], _oihw_strides(ws),
+                             scale_imm=0.25)
+        kept.append((g_y, g_c2, g_c1))
+        g_y = g_x
+    if grads is not None:
+        co.wgrad_run([ctx["xcol"]], [(0, 0, 0, 0)], g_y, grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
+        K.pool(g_y, None, shift=0, colsum=grads["img_forward.0.bias"])
+    if cots is not None:
+        cots.update(blocks=list(reversed(kept)), x0=g_y)
+    if not need_gx:
+        return None
+    hh = g_y.shape[1]
+    gx = torch.empty(n, 3, hh, hh, device=dev, dtype=F32)
+    co.conv_run([g_y], co.taps_3x3_dgrad(16), pk.w0_d, 16, None, out_nchw=gx, co_valid=3)
+    return gx
+
+
+def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tensor,
+                  rowscale: Optional[torch.Tensor], grads: dict) -> torch.Tensor:
+    """Tangent-forward sweep with frozen LeakyReLU masks: pushes the tangent image (scaled per sample by
+    rowscale) through the linearised trunk and accumulates, per conv, wgrad(tangent input, first-order
+    cotangent at its output) into grads -- exactly the parameter gradient of <tangent, d logits/d image>
+    (aten::_convolution_double_backward at deep_fusion_gan/model.py:207 without the zero-gradient waste).
+    Bias gradients stay zero (gotcha G3).  Returns the tangent of the embeds (NHWC bf16)."""
+    n, _, h, w = t_img.shape
+    dev = t_img.device
+    e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
+    tcol = e(n, h, w, 32)
+    K.im2col3(t_img, tcol, rowscale=rowscale)
+    t_x = e(n, h, w, pk.n_c)
+    co.conv_run([tcol], co.taps_1x1(), pk.w0_f, pk.n_c, t_x)
+    co.wgrad_run([tcol], [(0, 0, 0, 0)], cots["x0"], grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
+    for (p, cin, cout, sc), b, (x, c1, r), (c_y, c_c2, c_c1) in zip(pk.plan, pk.blocks, ctx["saved"],
+                                                                  cots["blocks"]):
+        h, w = h // 2, w // 2
+        pv = co.parity_views(t_x)
+        t_s = e(n, h, w, cout)
+        if sc:
+            co.conv_run(pv, TAPS_POOL, b["ws_f"], cout, t_s)
+            co.wgrad_run(pv, TAPS_POOL, c_y, grads[p + ".scale_conv.weight"],
+                         _oihw_strides(params[p + ".scale_conv.weight"]), scale_imm=0.25)
+        else:
+            K.pool(t_x, t_s, shift=1, scale=0.25)
+        t_c1 = e(n, h, w, cout)
+        co.conv_run(pv, co.taps_4x4s2(cout), b["w4_f"], cout, t_c1, mask_src=c1)
+        co.wgrad_run(pv, TAPS4_ID, c_c1, grads[p + ".residual_conv.0.weight"],
+                     _oihw_strides(params[p + ".residual_conv.0.weight"]))
+        t_y, t_r = e(n, h, w, cout), e(n, h, w, cout)
+        co.conv_run([t_c1], co.taps_3x3(cout), b["w3_f"], cout, t_y, mask_src=r, aux=t_r,
+                    scale_dev=params[p + ".gamma"], addend=t_s)
+        co.wgrad_run([t_c1], TAPS3_ID, c_c2, grads[p + ".residual_conv.2.weight"],
+                     _oihw_strides(params[p + ".residual_conv.2.weight"]))
+        K.dot(c_y, t_r, grads[p + ".gamma"])
+        t_x = t_y
+    return t_x
+
+
+# ------------------------------------------------------------------------------------------------ head
+def head_forward(pk: DPacked, params, embed: torch.Tensor, sent: torch.Tensor, ctx: Optional[dict] = None,
+                 sscale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """discriminator/model.py:43-59.  embed fp32 NCHW [b,16*n_c,4,4], sent fp32 [b,256] -> logits fp32 [b]."""
+    if embed.dim() != 4 or tuple(embed.shape[2:]) != (4, 4) or sent.shape[-1] != SENT_DIM or \
+            embed.shape[1] + SENT_DIM != pk.ccat or sent.shape[0] != embed.shape[0]:
+        raise RuntimeError(f"Sizes of tensors must match: embed {tuple(embed.shape)} / sentence "
+                           f"{tuple(sent.shape)} (discriminator/model.py:49-54)")
+    b = embed.shape[0]
+    dev = embed.device
+    cat = torch.empty(b, 4, 4, pk.ccat, device=dev, dtype=BF16)
+    K.head_cat(embed, sent, cat, sscale=sscale)
+    hid = torch.empty(b, 4, 4, pk.ch, device=dev, dtype=BF16)
+    co.conv_run([cat], co.taps_3x3(pk.ch), pk.wh_f, pk.ch, hid, lrelu_pre=True)
+    logits = torch.empty(b, device=dev, dtype=F32)
+    K.head_out(hid, params["img_sentence_forward.2.weight"], logits)
+    if ctx is not None:
+        ctx.update(cat=cat, hid=hid, b=b)
+    return logits
+
+
+def head_backward(pk: DPacked, params, ctx: dict, g_logit: Optional[torch.Tensor], grads: Optional[dict],
+                  need_sent: bool, cots: Optional[dict] = None):
+    """g_logit fp32 [b] (None = ones).  Returns (g_embed fp32 NCHW, g_sent fp32 [b,256] or None)."""
+    b, cat, hid = ctx["b"], ctx["cat"], ctx["hid"]
+    dev = cat.device
+    w2 = params["img_sentence_forward.2.weight"]
+    g_hid = torch.empty_like(hid)
+    K.head_out_bwd(g_logit, hid, hid, w2, g_hid,
+                   grads["img_sentence_forward.2.weight"] if grads is not None else None)
+    g_cat = torch.empty_like(cat)
+    co.conv_run([g_hid], co.taps_3x3_dgrad(pk.ccat), pk.wh_d, pk.ccat, g_cat)
+    if grads is not None:
+        co.wgrad_run([cat], TAPS3_ID, g_hid, grads["img_sentence_forward.0.weight"],
+                     _oihw_strides(params["img_sentence_forward.0.weight"]))
+    ce = pk.ccat - SENT_DIM
+    g_embed = torch.empty(b, ce, 4, 4, device=dev, dtype=F32)
+    g_sent = torch.empty(b, SENT_DIM, device=dev, dtype=F32) if need_sent else None
+    K.head_cat_bwd(g_cat, g_embed, g_sent)
+    if cots is not None:
+        cots.update(hid=g_hid, logit=g_logit)
+    return g_embed, g_sent
+
+
+def head_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_embed: torch.Tensor, t_sent: torch.Tensor,
+                 sscale: Optional[torch.Tensor], grads: dict) -> torch.Tensor:
+    """Tangent sweep of the head (second half of App. C-3).  t_embed fp32 NCHW, t_sent fp32 [b,256] (scaled per
+    sample by sscale).  Accumulates the two head weight gradients, returns the tangent logits fp32 [b]."""
+    b, hid = ctx["b"], ctx["hid"]
+    dev = hid.device
+    t_cat = torch.empty_like(ctx["cat"])
+    K.head_cat(t_embed, t_sent, t_cat, sscale=sscale)
+    t_hid = torch.empty_like(hid)
+    co.conv_run([t_cat], co.taps_3x3(pk.ch), pk.wh_f, pk.ch, t_hid, mask_src=hid)
+    co.wgrad_run([t_cat], TAPS3_ID, cots["hid"], grads["img_sentence_forward.0.weight"],
+                 _oihw_strides(params["img_sentence_forward.0.weight"]))
+    K.head_out_bwd(cots["logit"], None, t_hid, params["img_sentence_forward.2.weight"], None,
+                   grads["img_sentence_forward.2.weight"])
+    t_logit = torch.empty(b, device=dev, dtype=F32)
+    K.head_out(t_hid, params["img_sentence_forward.2.weight"], t_logit)
+    return t_logit
+
+
+def embeds_to_nchw(emb: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = emb.shape
+    out = torch.empty(n, c, h, w, device=emb.device, dtype=F32)
+    K.nhwc_to_nchw(emb, out)
+    return out
+
+
+def embeds_to_nhwc(emb: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = emb.shape
+    out = torch.empty(n, h, w, c, device=emb.device, dtype=BF16)
+    K.nchw_to_nhwc(emb.contiguous(), out)
+    return out

@@ -1,0 +1,200 @@
+"""Thin torch-tensor wrappers over the pointwise / MLP / packing / optimiser entry points of the C ABI
+(include/dfgan_b200.h).  Every function makes exactly one C call on the current CUDA stream; there is no
+fallback path -- a missing library or a non-CUDA tensor raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib_decl import LinearItem
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _s() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _nhwc(t: torch.Tensor):
+    assert t.is_cuda and t.dtype == BF16 and t.dim() == 4 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    return t.shape
+
+
+def _call(name: str, *args) -> None:
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def affine2_fwd(x, out, tables, tab_stride):
+    n, h, w, c = _nhwc(x)
+    _nhwc(out)
+    ga, ba, gb, bb = tables
+    _call("dfgan_affine2_fwd", _p(x), _p(out), _p(ga), _p(ba), _p(gb), _p(bb), tab_stride, n, h * w, c, _s())
+
+
+def affine2_bwd(g_a, x, gx, tables, dtables, tab_stride, *, g_add=None, gscale=None, dot=None, colsum=None):
+    n, h, w, c = _nhwc(x)
+    assert g_a.shape == x.shape and gx.shape == x.shape
+    _nhwc(g_a), _nhwc(gx)
+    if g_add is not None:
+        assert g_add.shape == x.shape
+        _nhwc(g_add)
+    ga, ba, gb, bb = tables
+    dga, dba, dgb, dbb = dtables
+    _call("dfgan_affine2_bwd", _p(g_a), _p(x), _p(g_add), _p(gx), _p(ga), _p(ba), _p(gb), _p(bb), _p(dga),
+          _p(dba), _p(dgb), _p(dbb), tab_stride, _p(gscale), _p(dot), _p(colsum), n, h * w, c, _s())
+
+
+def pool(x, out=None, *, shift=1, scale=1.0, colsum=None, cs_dev=None, cs_imm=1.0):
+    n, h, w, c = _nhwc(x)
+    ho, wo = h >> shift, w >> shift
+    if out is not None:
+        assert tuple(_nhwc(out)) == (n, ho, wo, c)
+    _call("dfgan_pool", _p(x), _p(out), _p(colsum), _p(cs_dev), cs_imm, n, ho, wo, c, shift, scale, _s())
+
+
+def dres_bwd(g_y, r, g_pre, gamma, dgamma=None, colsum=None):
+    n, h, w, c = _nhwc(g_y)
+    assert r.shape == g_y.shape and g_pre.shape == g_y.shape
+    _nhwc(r), _nhwc(g_pre)
+    _call("dfgan_dres_bwd", _p(g_y), _p(r), _p(g_pre), _p(gamma), _p(dgamma), _p(colsum), n, h * w, c, _s())
+
+
+def dot(a, b, out, scale=1.0):
+    assert a.dtype == BF16 and b.dtype == BF16 and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    _call("dfgan_dot", _p(a), _p(b), a.numel(), _p(out), scale, _s())
+
+
+def im2col3(img, out, rowscale=None):
+    assert img.is_cuda and img.dtype == F32 and img.is_contiguous() and img.shape[1] == 3
+    n, _, h, w = img.shape
+    assert tuple(_nhwc(out)) == (n, h, w, 32)
+    _call("dfgan_im2col3", _p(img), _p(rowscale), _p(out), n, h, w, _s())
+
+
+def tanh_bwd_pack(g_img, img, out, dbias=None):
+    assert g_img.dtype == F32 and img.dtype == F32 and g_img.is_contiguous() and img.is_contiguous()
+    n, _, h, w = img.shape
+    assert tuple(_nhwc(out)) == (n, h, w, 32)
+    _call("dfgan_tanh_bwd_pack", _p(g_img), _p(img), _p(out), _p(dbias), n, h * w, _s())
+
+
+def nchw_to_nhwc(x, out):
+    """fp32 [N,C,H,W] -> bf16 [N,H,W,C]"""
+    assert x.dtype == F32 and x.is_contiguous() and x.is_cuda
+    n, c, h, w = x.shape
+    assert tuple(_nhwc(out)) == (n, h, w, c)
+    _call("dfgan_nchw_to_nhwc", _p(x), _p(out), n, c, h * w, _s())
+
+
+def nhwc_to_nchw(x, out, accumulate=False):
+    n, h, w, c = _nhwc(x)
+    assert out.dtype == F32 and out.is_contiguous() and tuple(out.shape) == (n, c, h, w)
+    _call("dfgan_nhwc_to_nchw", _p(x), _p(out), n, c, h * w, int(accumulate), _s())
+
+
+def rowsq(x, out):
+    assert x.dtype == F32 and x.is_contiguous() and out.dtype == F32
+    n = x.shape[0]
+    _call("dfgan_rowsq", _p(x), n, x.numel() // n, _p(out), _s())
+
+
+def head_cat(embed, sent, cat, sscale=None):
+    b, ce = embed.shape[0], embed.shape[1]
+    assert embed.dtype == F32 and embed.is_contiguous() and tuple(embed.shape[2:]) == (4, 4)
+    assert sent.dtype == F32 and sent.is_contiguous() and sent.shape[0] == b
+    assert tuple(_nhwc(cat)) == (b, 4, 4, ce + sent.shape[1])
+    _call("dfgan_head_cat", _p(embed), _p(sent), _p(sscale), _p(cat), b, ce, sent.shape[1], _s())
+
+
+def head_cat_bwd(g_cat, g_embed, g_sent):
+    b = g_cat.shape[0]
+    ce = g_embed.shape[1]
+    cs = g_cat.shape[3] - ce
+    assert g_embed.dtype == F32 and g_embed.is_contiguous()
+    if g_sent is not None:
+        assert g_sent.dtype == F32 and g_sent.is_contiguous() and tuple(g_sent.shape) == (b, cs)
+    _call("dfgan_head_cat_bwd", _p(g_cat), _p(g_embed), _p(g_sent), b, ce, cs, _s())
+
+
+def head_out(hid, w2, logits):
+    b, _, _, ch = _nhwc(hid)
+    assert w2.dtype == F32 and w2.is_contiguous() and w2.numel() == 16 * ch and logits.numel() == b
+    _call("dfgan_head_out", _p(hid), _p(w2), _p(logits), b, ch, _s())
+
+
+def head_out_bwd(g_logit, hid, act, w2, g_hid, dw2):
+    ref = hid if hid is not None else act
+    b, _, _, ch = _nhwc(ref)
+    _call("dfgan_head_out_bwd", _p(g_logit), _p(hid), _p(act), _p(w2), _p(g_hid), _p(dw2), b, ch, _s())
+
+
+# ------------------------------------------------------------------------------------ batched linears
+class LinearTable:
+    """Device-resident table of 64-output work items for dfgan_linear_batched.  Built once from the
+    pointers of the tensors involved; the tensors must stay alive and in place while the table is used."""
+
+    def __init__(self, problems: Sequence[dict], mode: int, device):
+        items = []
+        self.k_max, self.n_out_max = 1, 1
+        for pr in problems:
+            k, n_out = pr["k"], pr["n_out"]
+            self.k_max, self.n_out_max = max(self.k_max, k), max(self.n_out_max, n_out)
+            span = k if mode == 1 else n_out
+            for o0 in range(0, span, 64):
+                items.append(LinearItem(pr["inp"], pr["in_stride"], pr["w"], pr.get("bias"), pr["out"],
+                                        pr["out_stride"], pr.get("mask"), k, n_out, o0, int(pr.get("relu", 0))))
+        self.n = len(items)
+        arr = (LinearItem * self.n)(*items)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.dev = raw.to(device)
+        self.mode = mode
+
+    def run(self, batch: int) -> None:
+        _call("dfgan_linear_batched", self.dev.data_ptr(), self.n, batch, self.k_max, self.n_out_max,
+              self.mode, _s())
+
+
+# ------------------------------------------------------------------------------------ packing / optimiser
+def pack_weights(w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False):
+    """fp32 OIHW -> bf16 [n_slots*rows_pad, cols_pad].  slots: list of lists of source tap indices (default:
+    one slot per tap).  as_matrix: treat [Co, Ci, kh, kw] as [Co, Ci*kh*kw, 1, 1] (stem im2col weights)."""
+    assert w.dtype == F32 and w.is_contiguous() and w.is_cuda and out.dtype == BF16 and out.is_contiguous()
+    co, ci, kh, kw = w.shape
+    if as_matrix:
+        ci, kh, kw = ci * kh * kw, 1, 1
+    kk = kh * kw
+    if slots is None:
+        slots = [[t] for t in range(kk)]
+    rows = ci if transpose else co
+    cols = co if transpose else ci
+    rows_pad, cols_pad = rows_pad or rows, cols_pad or cols
+    assert out.numel() == len(slots) * rows_pad * cols_pad, (out.shape, len(slots), rows_pad, cols_pad)
+    flat = (C.c_int8 * (len(slots) * 4))(*[(s[j] if j < len(s) else -1) for s in slots for j in range(4)])
+    _call("dfgan_pack_weights", _p(w), _p(out), co, ci, kk, int(transpose), rows_pad, cols_pad, len(slots),
+          C.cast(flat, C.c_void_p), scale, _s())
+
+
+def unfold_subpixel_wgrad(folded, dw):
+    co, ci = dw.shape[0], dw.shape[1]
+    assert folded.dtype == F32 and folded.numel() == 16 * co * ci and dw.dtype == F32 and dw.is_contiguous()
+    _call("dfgan_unfold_subpixel_wgrad", _p(folded), _p(dw), co, ci, _s())
+
+
+def sqnorm(g, out):
+    assert g.dtype == F32 and g.is_contiguous() and out.dtype == F32
+    _call("dfgan_sqnorm", _p(g), g.numel(), _p(out), _s())
+
+
+def adam_step(p, g, m, v, sumsq, step, *, lr, gscale=1.0, max_norm=5.0, b1=0.0, b2=0.9, eps=1e-8):
+    for t in (p, g, m, v):
+        assert t.dtype == F32 and t.is_contiguous() and t.numel() == p.numel()
+    assert step.dtype == torch.int32
+    _call("dfgan_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(sumsq), _p(step), gscale, max_norm, lr,
+          b1, b2, eps, _s())

@@ -48,16 +48,22 @@ typedef struct dfgan_tap {
  *   acc[n,h,w,co] = sum_t sum_ci src[t.src][n, h+t.dy, w+t.dx, ci] * wpack[t.wrow + co][ci]
  *   v   = acc + bias[co]                      (bias optional)
  *   v   = lrelu_pre ? leaky_relu(v, slope) : v
- *   aux[n,h,w,co] = v                         (aux optional, same strides as out)
+ *   v  *= (mask_src[n,h,w,co] > 0 ? 1 : slope)                       (mask_src optional, out strides)
+ *   aux[n,h,w,co] = bf16(v)                   (aux optional, out strides)
  *   v   = v * scale_imm * (scale_dev ? *scale_dev : 1)
  *   v  += add_scale * addend[n, h>>add_shift, w>>add_shift, co]      (addend optional)
- *   v  *= (mask_src[n,h,w,co] > 0 ? 1 : slope)                       (mask_src optional, out strides)
- *   out[n,h,w,co] = bf16(v)   at out + n*out_sn + h*out_sh + w*out_sw + co
+ *   out_nchw[n][co][h][w] = tanh_out ? tanh(v) : v   for co < co_valid   (fp32 planar, optional)
+ *   out[n,h,w,co] = bf16(v)   at out + n*out_sn + h*out_sh + w*out_sw + co   (optional)
+ *   out2[n,h,w,co] = post(bf16(v))            (optional, out strides); post_mode 1: leaky_relu,
+ *        2: leaky_relu(gb*leaky_relu(ga*v+ba)+bb) with ga.. = tab_*[n*tab_stride + co]  (AffineBlock pair)
+ * At least one of out / aux / out2 / out_nchw must be given.
  * replaces: nn.Conv2d forward and the data-gradient half of aten::convolution_backward at
  *   generator/residual_block.py:16,21,25,40,47  discriminator/residual_block.py:11,13,19
  *   discriminator/model.py:31 ; the stride-2 conv is expressed with four parity views of the input,
  *   its data gradient with four output phases (strided out_s*), the fused epilogue covers
- *   generator/residual_block.py:59, discriminator/residual_block.py:12,14,30 and F.leaky_relu backward.
+ *   generator/residual_block.py:59, discriminator/residual_block.py:12,14,30 and F.leaky_relu backward;
+ *   post_mode 2 covers generator/residual_block.py:36-39,43-46 + generator/fusion_block.py:37-39 of the
+ *   NEXT convolution's input, out_nchw+tanh covers generator/model.py:28-29.
  */
 typedef struct dfgan_conv_desc {
   dfgan_view4 src[DFGAN_MAX_SRC];
@@ -81,6 +87,12 @@ typedef struct dfgan_conv_desc {
   const void* mask_src;
   int32_t n_tile_hint; /* 0 = auto */
   int32_t max_ctas;    /* 0 = one per SM */
+  void* out2;
+  int32_t post_mode;
+  const float *tab_ga, *tab_ba, *tab_gb, *tab_bb; /* fp32 [N][tab_stride] gamma/beta tables */
+  int64_t tab_stride;
+  float* out_nchw;
+  int32_t co_valid, tanh_out;
 } dfgan_conv_desc;
 
 int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream);
@@ -102,9 +114,91 @@ typedef struct dfgan_wgrad_desc {
   const float* scale_dev;
   float scale_imm;
   int32_t k_splits; /* 0 = auto */
+  int32_t ci_valid, co_valid; /* 0 = all; rows/cols at or beyond are padding and are not written */
 } dfgan_wgrad_desc;
 
 int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------------
+ * Pointwise / reduction kernels (csrc/pointwise.cu).  Activations: contiguous NHWC bf16 [N][HW][C], C % 8 == 0.
+ * gamma/beta tables: fp32 [N][tab_stride], the pointer already offset to the block's first column.
+ */
+/* out = lrelu(gb*lrelu(ga*x+ba)+bb).  replaces: generator/residual_block.py:36-39,43-46 + fusion_block.py:37-39 */
+int dfgan_affine2_fwd(const void* x, void* out, const float* ga, const float* ba, const float* gb,
+                      const float* bb, int64_t tab_stride, int N, int HW, int C, dfgan_stream_t st);
+/* Backward of the pair incl. the per-(n,c) reductions d_ga.. (atomically accumulated), optional gradient scale
+ * (*gscale), optional residual-gate dot product dot += <g_a, lrelu(u2)>, optional added gradient g_add and
+ * optional column sum of the result.  replaces: autograd of the same lines (mul/add/leaky_relu backward). */
+int dfgan_affine2_bwd(const void* g_a, const void* x, const void* g_add, void* gx, const float* ga,
+                      const float* ba, const float* gb, const float* bb, float* d_ga, float* d_ba,
+                      float* d_gb, float* d_bb, int64_t tab_stride, const float* gscale, float* dot,
+                      float* colsum, int N, int HW, int C, dfgan_stream_t st);
+/* out[n,i,j,c] = scale * sum over the (1<<shift)^2 window of x ; colsum[c] += cs_imm*(*cs_dev)*sum x.
+ * replaces: F.avg_pool2d (discriminator/residual_block.py:27), upsample_nearest2d backward (generator/model.py:40),
+ * bias-gradient column sums of aten::convolution_backward. */
+int dfgan_pool(const void* x, void* out, float* colsum, const float* cs_dev, float cs_imm, int N, int Ho,
+               int Wo, int C, int shift, float scale, dfgan_stream_t st);
+/* g_pre = g_y * *gamma * lrelu'(r) ; *dgamma += <g_y, r> ; colsum[c] += sum g_y.
+ * replaces: backward of `shortcut + gamma * residual` and the trailing LeakyReLU, discriminator/residual_block.py:14,30 */
+int dfgan_dres_bwd(const void* g_y, const void* r, void* g_pre, const float* gamma, float* dgamma,
+                   float* colsum, int N, int HW, int C, dfgan_stream_t st);
+/* *out += scale * <a, b>  (n bf16 elements, n % 8 == 0) */
+int dfgan_dot(const void* a, const void* b, int64_t n, float* out, float scale, dfgan_stream_t st);
+/* Stem im2col: NCHW fp32 image [N,3,H,W] (optionally scaled per sample) -> NHWC bf16 [N,H,W,32], channel
+ * ci*9+r*3+s = img[ci][h+r-1][w+s-1].  replaces: the input gather of nn.Conv2d(3,n_c,3,1,1), discriminator/model.py:13 */
+int dfgan_im2col3(const float* img, const float* rowscale, void* out, int N, int H, int W, dfgan_stream_t st);
+/* g_t = g_img*(1-img^2) packed NHWC bf16 [N,HW,32] (3 real channels); dbias[0..2] += sum.  replaces: tanh backward, generator/model.py:29 */
+int dfgan_tanh_bwd_pack(const float* g_img, const float* img, void* out, float* dbias, int N, int HW,
+                        dfgan_stream_t st);
+/* fp32 [N][C][HW] <-> bf16 [N][HW][C] (API-boundary layout changes: generator/model.py:37, discriminator/model.py:36-41) */
+int dfgan_nchw_to_nhwc(const float* in, void* out, int N, int C, int HW, dfgan_stream_t st);
+int dfgan_nhwc_to_nchw(const void* in, float* out, int N, int C, int HW, int accumulate, dfgan_stream_t st);
+/* out[n] += sum_i x[n][i]^2   (deep_fusion_gan/model.py:82) */
+int dfgan_rowsq(const float* x, int N, int64_t row_len, float* out, dfgan_stream_t st);
+/* Logit head (discriminator/model.py:43-59): concat builder, its backward, and the final 4x4 valid conv. */
+int dfgan_head_cat(const float* embed, const float* sent, const float* sscale, void* cat, int B, int Ce,
+                   int Cs, dfgan_stream_t st);
+int dfgan_head_cat_bwd(const void* g_cat, float* g_embed, float* g_sent, int B, int Ce, int Cs,
+                       dfgan_stream_t st);
+int dfgan_head_out(const void* hid, const float* w2, float* logits, int B, int Ch, dfgan_stream_t st);
+int dfgan_head_out_bwd(const float* g_logit, const void* hid, const void* act, const float* w2, void* g_hid,
+                       float* dw2, int B, int Ch, dfgan_stream_t st);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Batched small linears (csrc/mlp_optim.cu): one launch over a DEVICE table of 64-output work items.
+ *   mode 0: out[b,o] = act(sum_k in[b,k]*w[o,k] + bias[o])            o in [o0, o0+64)
+ *   mode 1: in[b,k]  = relu'(mask[b,k]) * sum_o out[b,o]*w[o,k]        k in [o0, o0+64)   (`in` is written)
+ *   mode 2: w[o,k]  += sum_b out[b,o]*in[b,k] ; bias[o] += sum_b out[b,o]   (`w`,`bias` are written)
+ * replaces: the 113 aten::addmm of Generator.forward (generator/fusion_block.py:8-18,34-35; generator/model.py:34)
+ * and their autograd.
+ */
+typedef struct dfgan_linear_item {
+  const float* in;
+  int64_t in_stride;
+  const float* w;
+  const float* bias;
+  float* out;
+  int64_t out_stride;
+  const float* mask;
+  int32_t k, n_out, o0, relu;
+} dfgan_linear_item;
+int dfgan_linear_batched(const dfgan_linear_item* items_dev, int n_items, int B, int k_max, int n_out_max,
+                         int mode, dfgan_stream_t st);
+
+/* fp32 OIHW weights -> bf16 GEMM operand [n_slots][rows_pad][cols_pad]; slot s = scale * sum of the source
+ * taps slot_taps[s][0..3] (-1 = unused; HOST array); transpose 0: rows=co, cols=ci; 1: rows=ci, cols=co. */
+int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int transpose, int rows_pad,
+                       int cols_pad, int n_slots, const int8_t* slot_taps, float scale, dfgan_stream_t st);
+/* dw[co][ci][3][3] += un-folded sub-pixel weight gradient folded[16][co][ci]. */
+int dfgan_unfold_subpixel_wgrad(const float* folded, float* dw, int Co, int Ci, dfgan_stream_t st);
+
+/* *out += sum g^2 ; then clip (global L2 norm, max_norm) + Adam over a flat buffer.  step: device int (>= 1).
+ * replaces: clip_grad_norm_ + Adam.step, deep_fusion_gan/model.py:42-43,195-197,208-210,226-228 */
+int dfgan_sqnorm(const float* g, int64_t n, float* out, dfgan_stream_t st);
+int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
+                    const int* step, float gscale, float max_norm, float lr, float b1, float b2, float eps,
+                    dfgan_stream_t st);
 
 /* Library identification: version = major*10000 + minor*100 + patch; arch string is "sm_100a". */
 int dfgan_version(void);

@@ -30,6 +30,19 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 
 
+def _pack(w, transpose=False, **kw):
+    import torch
+    from gan_codes_b200 import kernels as K
+    co_, ci, kh, kw_ = w.shape
+    rows = ci if transpose else co_
+    cols = co_ if transpose else ci
+    slots = kw.get("slots")
+    n_slots = len(slots) if slots else kh * kw_
+    out = torch.empty(n_slots * kw.get("rows_pad", rows), kw.get("cols_pad", cols), device=w.device, dtype=torch.bfloat16)
+    K.pack_weights(w.float().contiguous(), out, transpose=transpose, **kw)
+    return out
+
+
 def _run_fprop3(N, C, K, H, W, **kw):
     torch = _setup()
     import torch.nn.functional as F
@@ -39,7 +52,7 @@ def _run_fprop3(N, C, K, H, W, **kw):
     b = torch.randn(K, device="cuda")
     ref = F.conv2d(x.float(), w.float(), b, padding=1)
     out = torch.empty(N, H, W, K, device="cuda", dtype=torch.bfloat16)
-    co.conv_run([_nhwc(x)], co.taps_3x3(K), co.pack_fwd(w.float()), K, out, bias=b, **kw)
+    co.conv_run([_nhwc(x)], co.taps_3x3(K), _pack(w), K, out, bias=b, **kw)
     torch.cuda.synchronize()
     err = _rel(out.permute(0, 3, 1, 2), ref)
     print(f"fprop3 N{N} C{C} K{K} {H}x{W} {kw}: rel {err:.3e}")
@@ -74,7 +87,7 @@ def fprop4s2():
         w = (torch.randn(K, C, 4, 4, device="cuda") / (4 * C ** 0.5)).bfloat16()
         ref = F.leaky_relu(F.conv2d(x.float(), w.float(), None, stride=2, padding=1), 0.2)
         out = torch.empty(N, H // 2, H // 2, K, device="cuda", dtype=torch.bfloat16)
-        co.conv_run(co.parity_views(_nhwc(x)), co.taps_4x4s2(K), co.pack_fwd(w.float()), K, out, lrelu_pre=True)
+        co.conv_run(co.parity_views(_nhwc(x)), co.taps_4x4s2(K), _pack(w), K, out, lrelu_pre=True)
         torch.cuda.synchronize()
         err = _rel(out.permute(0, 3, 1, 2), ref)
         print(f"fprop4s2 N{N} C{C} K{K} {H}: rel {err:.3e}")
@@ -93,7 +106,7 @@ def dgrad():
         g = torch.randn(N, K, H, H, device="cuda").bfloat16()
         ref = F.conv_transpose2d(g.float(), w.float(), padding=1)
         out = torch.empty(N, H, H, C, device="cuda", dtype=torch.bfloat16)
-        co.conv_run([_nhwc(g)], co.taps_3x3_dgrad(C), co.pack_dgrad(w.float()), C, out)
+        co.conv_run([_nhwc(g)], co.taps_3x3_dgrad(C), _pack(w, True), C, out)
         torch.cuda.synchronize()
         err = _rel(out.permute(0, 3, 1, 2), ref)
         print(f"dgrad3 N{N} C{C} K{K} {H}: rel {err:.3e}")
@@ -103,7 +116,7 @@ def dgrad():
         g2 = torch.randn(N, K, H // 2, H // 2, device="cuda").bfloat16()
         ref = F.conv_transpose2d(g2.float(), w4.float(), stride=2, padding=1)
         out = torch.zeros(N, H, H, C, device="cuda", dtype=torch.bfloat16)
-        wp = co.pack_dgrad(w4.float())
+        wp = _pack(w4, True)
         g2n = _nhwc(g2)
         for a in (0, 1):
             for c in (0, 1):
@@ -128,17 +141,231 @@ def epilogue():
     sc = torch.randn(N, K, H // 2, H // 2, device="cuda").bfloat16()
     msk = torch.randn(N, K, H, H, device="cuda").bfloat16()
     pre = F.leaky_relu(F.conv2d(x.float(), w.float(), b, padding=1), 0.2)
+    pre = pre * torch.where(msk.float() > 0, 1.0, 0.2)
     ref = pre * gamma * 2.0 + 0.5 * F.interpolate(sc.float(), scale_factor=2)
-    ref = ref * torch.where(msk.float() > 0, 1.0, 0.2)
     out = torch.empty(N, H, H, K, device="cuda", dtype=torch.bfloat16)
     aux = torch.empty_like(out)
-    co.conv_run([_nhwc(x)], co.taps_3x3(K), co.pack_fwd(w.float()), K, out, bias=b, lrelu_pre=True,
+    co.conv_run([_nhwc(x)], co.taps_3x3(K), _pack(w), K, out, bias=b, lrelu_pre=True,
                 scale_dev=gamma, scale_imm=2.0, aux=aux, addend=_nhwc(sc), add_shift=1, add_scale=0.5,
                 mask_src=_nhwc(msk))
     torch.cuda.synchronize()
     e1, e2 = _rel(out.permute(0, 3, 1, 2), ref), _rel(aux.permute(0, 3, 1, 2), pre)
     print(f"epilogue: out rel {e1:.3e} aux rel {e2:.3e}")
     return e1 < 8e-3 and e2 < 8e-3
+
+
+@case
+def subpixel():
+    """upsample -> conv3x3 as four phase convs (fwd), its data gradient and its folded weight gradient."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co, kernels as K
+    ok = True
+    for (N, C, Kc, H) in [(2, 64, 32, 16), (3, 256, 128, 8), (2, 128, 64, 32)]:
+        x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        w = (torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5))
+        b = torch.randn(Kc, device="cuda")
+        xr = x.float().requires_grad_()
+        wr = w.clone().requires_grad_()
+        ref = F.conv2d(F.interpolate(xr, scale_factor=2), wr, b, padding=1)
+        g = torch.randn_like(ref).bfloat16()
+        gx_ref, gw_ref = torch.autograd.grad(ref, (xr, wr), g.float())
+        slots = co.subpixel_slots()
+        wf, wd = _pack(w, slots=slots), _pack(w, True, slots=slots)
+        out = torch.empty(N, 2 * H, 2 * H, Kc, device="cuda", dtype=torch.bfloat16)
+        xn = _nhwc(x)
+        for a in (0, 1):
+            for c in (0, 1):
+                co.conv_run([xn], co.taps_subpixel_fwd(Kc, a, c), wf, Kc, out[:, a::2, c::2, :], grid=(N, H, H), bias=b)
+        gn = _nhwc(g)
+        gx = torch.empty(N, H, H, C, device="cuda", dtype=torch.bfloat16)
+        co.conv_run([gn[:, a::2, c::2, :] for a in (0, 1) for c in (0, 1)], co.taps_subpixel_dgrad(C), wd, C, gx)
+        folded = torch.zeros(16, Kc, C, device="cuda")
+        for a in (0, 1):
+            for c in (0, 1):
+                co.wgrad_run([xn], co.taps_subpixel_wgrad(a, c), gn[:, a::2, c::2, :], folded, (C, 1, Kc * C))
+        dw = torch.zeros(Kc, C, 3, 3, device="cuda")
+        K.unfold_subpixel_wgrad(folded, dw)
+        torch.cuda.synchronize()
+        e = (_rel(out.permute(0, 3, 1, 2), ref), _rel(gx.permute(0, 3, 1, 2), gx_ref), _rel(dw, gw_ref))
+        print(f"subpixel N{N} C{C} K{Kc} {H}: fwd {e[0]:.3e} dgrad {e[1]:.3e} wgrad {e[2]:.3e}")
+        ok &= max(e) < 8e-3
+    return ok
+
+
+@case
+def edge():
+    """image-boundary convs: stem via im2col (fwd / wgrad / dgrad to fp32 NCHW) and conv_out (+tanh)."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co, kernels as K
+    N, H = 2, 64
+    img = torch.randn(N, 3, H, H, device="cuda")
+    w = torch.randn(32, 3, 3, 3, device="cuda") / 5
+    b = torch.randn(32, device="cuda")
+    imgr, wr = img.clone().requires_grad_(), w.clone().requires_grad_()
+    ref = F.conv2d(imgr, wr, b, padding=1)
+    g = torch.randn_like(ref).bfloat16()
+    gi_ref, gw_ref = torch.autograd.grad(ref, (imgr, wr), g.float())
+    xcol = torch.empty(N, H, H, 32, device="cuda", dtype=torch.bfloat16)
+    K.im2col3(img, xcol)
+    w0f = torch.empty(32, 32, device="cuda", dtype=torch.bfloat16)
+    K.pack_weights(w, w0f, as_matrix=True, cols_pad=32)
+    out = torch.empty(N, H, H, 32, device="cuda", dtype=torch.bfloat16)
+    co.conv_run([xcol], co.taps_1x1(), w0f, 32, out, bias=b)
+    dw = torch.zeros_like(w)
+    gn = _nhwc(g)
+    co.wgrad_run([xcol], [(0, 0, 0, 0)], gn, dw, (27, 1, 0), ci_valid=27)
+    w0d = _pack(w, True, rows_pad=16)
+    gi = torch.empty(N, 3, H, H, device="cuda")
+    co.conv_run([gn], co.taps_3x3_dgrad(16), w0d, 16, None, out_nchw=gi, co_valid=3)
+    torch.cuda.synchronize()
+    e = [_rel(out.permute(0, 3, 1, 2), ref), _rel(dw, gw_ref), _rel(gi, gi_ref)]
+    print(f"stem: fwd {e[0]:.3e} wgrad {e[1]:.3e} dgrad {e[2]:.3e}")
+    # conv_out: lrelu'd 32-ch input -> 3 ch + tanh, and its backward
+    x = torch.randn(N, 32, H, H, device="cuda").bfloat16()
+    wo = torch.randn(3, 32, 3, 3, device="cuda") / 17
+    bo = torch.randn(3, device="cuda") / 3
+    xr, wor, bor = x.float().requires_grad_(), wo.clone().requires_grad_(), bo.clone().requires_grad_()
+    ref = torch.tanh(F.conv2d(xr, wor, bor, padding=1))
+    gimg = torch.randn_like(ref)
+    gx_ref, gwo_ref, gbo_ref = torch.autograd.grad(ref, (xr, wor, bor), gimg)
+    wof = _pack(wo, rows_pad=16)
+    bo16 = torch.zeros(16, device="cuda")
+    bo16[:3] = bo
+    o = torch.empty(N, 3, H, H, device="cuda")
+    xn = _nhwc(x)
+    co.conv_run([xn], co.taps_3x3(16), wof, 16, None, bias=bo16, out_nchw=o, co_valid=3, tanh_out=True)
+    g_t = torch.empty(N, H, H, 32, device="cuda", dtype=torch.bfloat16)
+    dbo = torch.zeros(3, device="cuda")
+    K.tanh_bwd_pack(gimg, o, g_t, dbias=dbo)
+    dwo = torch.zeros_like(wo)
+    co.wgrad_run([xn], [(0, r - 1, s - 1, r * 3 + s) for r in range(3) for s in range(3)], g_t, dwo, (288, 9, 1), co_valid=3)
+    wod = _pack(wo, True, cols_pad=32)
+    gx = torch.empty(N, H, H, 32, device="cuda", dtype=torch.bfloat16)
+    co.conv_run([g_t], co.taps_3x3_dgrad(32), wod, 32, gx)
+    torch.cuda.synchronize()
+    e2 = [_rel(o, ref), _rel(dwo, gwo_ref), _rel(dbo, gbo_ref), _rel(gx.permute(0, 3, 1, 2), gx_ref)]
+    print(f"conv_out: fwd {e2[0]:.3e} wgrad {e2[1]:.3e} dbias {e2[2]:.3e} dgrad {e2[3]:.3e}")
+    return max(e + e2) < 8e-3
+
+
+@case
+def pointwise():
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import kernels as K
+    ok = True
+    lr = lambda t: F.leaky_relu(t, 0.2)  # noqa: E731
+    for (N, H, C) in [(3, 16, 64), (2, 64, 32), (4, 4, 256)]:
+        T = 4 * C + 64
+        tab = torch.randn(N, T, device="cuda")
+        x = torch.randn(N, H, H, C, device="cuda").bfloat16()
+        g = torch.randn(N, H, H, C, device="cuda").bfloat16()
+        gadd = torch.randn(N, H, H, C, device="cuda").bfloat16()
+        tabs = tuple(tab[:, 32 + i * C: 32 + (i + 1) * C] for i in range(4))
+        xr = x.float().requires_grad_()
+        tr = [t.clone().requires_grad_() for t in tabs]
+        bc = lambda t: t[:, None, None, :]  # noqa: E731
+        u1 = bc(tr[0]) * xr + bc(tr[1])
+        a = lr(bc(tr[2]) * lr(u1) + bc(tr[3]))
+        gsc = torch.tensor([0.7], device="cuda")
+        grads = torch.autograd.grad(a, [xr] + tr, g.float() * gsc)
+        out = torch.empty_like(x)
+        K.affine2_fwd(x, out, tabs, T)
+        dtab = torch.zeros_like(tab)
+        dts = tuple(dtab[:, 32 + i * C: 32 + (i + 1) * C] for i in range(4))
+        gx = torch.empty_like(x)
+        dot = torch.zeros(1, device="cuda")
+        cs = torch.zeros(C, device="cuda")
+        K.affine2_bwd(g, x, gx, tabs, dts, T, g_add=gadd, gscale=gsc, dot=dot, colsum=cs)
+        torch.cuda.synchronize()
+        gx_ref = grads[0] + gadd.float()
+        e = [_rel(out, a), _rel(gx, gx_ref), _rel(dot, (g.float() * a).sum().reshape(1)), _rel(cs, gx_ref.sum((0, 1, 2)))]
+        e += [_rel(dts[i], grads[1 + i]) for i in range(4)]
+        print(f"affine2 N{N} H{H} C{C}: " + " ".join(f"{v:.2e}" for v in e))
+        ok &= max(e) < 8e-3
+        # pooling / dres
+        if H >= 2:
+            po = torch.empty(N, H // 2, H // 2, C, device="cuda", dtype=torch.bfloat16)
+            cs = torch.zeros(C, device="cuda")
+            K.pool(x, po, shift=1, scale=0.25, colsum=cs, cs_dev=gsc, cs_imm=2.0)
+            ref = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+            r = torch.randn(N, H, H, C, device="cuda").bfloat16()
+            gp = torch.empty_like(x)
+            dg = torch.zeros(1, device="cuda")
+            cs2 = torch.zeros(C, device="cuda")
+            K.dres_bwd(g, r, gp, gsc, dg, cs2)
+            d2 = torch.zeros(1, device="cuda")
+            K.dot(g, r, d2, 0.5)
+            torch.cuda.synchronize()
+            e = [_rel(po, ref), _rel(cs, 1.4 * x.float().sum((0, 1, 2))),
+                 _rel(gp, g.float() * 0.7 * torch.where(r.float() > 0, 1.0, 0.2)),
+                 _rel(dg, (g.float() * r.float()).sum().reshape(1)), _rel(cs2, g.float().sum((0, 1, 2))),
+                 _rel(d2, 0.5 * (g.float() * r.float()).sum().reshape(1))]
+            print(f"pool/dres N{N} H{H} C{C}: " + " ".join(f"{v:.2e}" for v in e))
+            ok &= max(e) < 8e-3
+    # layout + head + rowsq
+    emb = torch.randn(3, 512, 4, 4, device="cuda")
+    sent = torch.randn(3, 256, device="cuda")
+    ssc = torch.rand(3, device="cuda")
+    cat = torch.empty(3, 4, 4, 768, device="cuda", dtype=torch.bfloat16)
+    K.head_cat(emb, sent, cat, sscale=ssc)
+    ref = torch.cat((emb, (sent * ssc[:, None])[:, :, None, None].expand(-1, -1, 4, 4)), 1)
+    ge, gs = torch.empty(3, 512, 4, 4, device="cuda"), torch.empty(3, 256, device="cuda")
+    K.head_cat_bwd(cat, ge, gs)
+    hid = torch.randn(3, 4, 4, 64, device="cuda").bfloat16()
+    w2 = torch.randn(1, 64, 4, 4, device="cuda")
+    lg = torch.empty(3, device="cuda")
+    K.head_out(hid, w2, lg)
+    gl = torch.randn(3, device="cuda")
+    ghid = torch.empty_like(hid)
+    dw2 = torch.zeros_like(w2)
+    K.head_out_bwd(gl, hid, hid, w2, ghid, dw2)
+    rs = torch.zeros(3, device="cuda")
+    K.rowsq(emb, rs)
+    back = torch.empty(3, 4, 4, 512, device="cuda", dtype=torch.bfloat16)
+    K.nchw_to_nhwc(emb, back)
+    rt = torch.empty_like(emb)
+    K.nhwc_to_nchw(back, rt)
+    torch.cuda.synchronize()
+    hidn = hid.float().permute(0, 3, 1, 2)
+    e = [_rel(cat.permute(0, 3, 1, 2), ref), _rel(ge, cat.float().permute(0, 3, 1, 2)[:, :512]),
+         _rel(gs, cat.float()[..., 512:].sum((1, 2))), _rel(lg, (hidn * w2).sum((1, 2, 3))),
+         _rel(ghid.permute(0, 3, 1, 2), gl[:, None, None, None] * w2 * torch.where(hidn > 0, 1.0, 0.2)),
+         _rel(dw2, (gl[:, None, None, None] * hidn).sum(0, keepdim=True)), _rel(rs, (emb ** 2).sum((1, 2, 3))),
+         _rel(rt, emb)]
+    print("head/layout: " + " ".join(f"{v:.2e}" for v in e))
+    ok &= max(e) < 8e-3
+    return ok
+
+
+@case
+def optim():
+    torch = _setup()
+    from gan_codes_b200 import kernels as K
+    n = 1_000_003
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda") * 0.01
+    pr = p.clone().requires_grad_()
+    opt = torch.optim.Adam([pr], lr=4e-4, betas=(0.0, 0.9))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ok = True
+    for it in range(3):
+        gi = g * (it + 1)
+        pr.grad = gi.clone()
+        torch.nn.utils.clip_grad_norm_([pr], 5.0)
+        opt.step()
+        ss = torch.zeros(1, device="cuda")
+        K.sqnorm(gi, ss)
+        step += 1
+        K.adam_step(p, gi, m, v, ss, step, lr=4e-4)
+        torch.cuda.synchronize()
+        e = _rel(p - pr.detach(), torch.zeros_like(p)) if False else ((p - pr.detach()).abs().max() / 4e-4).item()
+        print(f"adam it{it}: max |dp| / lr = {e:.3e}, sumsq rel {abs(ss.item() - (gi ** 2).sum().item()) / (gi ** 2).sum().item():.2e}")
+        ok &= e < 1e-2
+    return ok
 
 
 @case
