@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""Headline benchmark: training images/s of one full DF-GAN iteration (D hinge step + MA-GP step + G step, three
+clip+Adam updates -- deep_fusion_gan/model.py:173-228) at 256x256, n_channels 32, batch 32 per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.  `value` = whole-job images/s
+with inputs resident in HBM; `e2e` = the same through DFGANTrainer.step with pinned HOST inputs and a device->host
+read of the three losses every step.  `roofline` is measured live with CUDA events around every launch of the
+dominant kernel; `cpu_baseline` times the oracle port of the reference's step on the host cores (rank 0, N=1).
+`--impl reference` times that CPU path alone (the reference is PyTorch-eager CPU code; it cannot travel to the GPU
+box, oracle/ is its pinned restatement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = 181.3   # algorithmic minimum of the full step, SURVEY 8(d) / BASELINE.md section 3
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def summary(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_step(batch: int, size: int, steps: int, warmup: int):
+    """The reference's training iteration on the host cores (oracle port), returns (img/s, cores, seconds)."""
+    import torch
+    from oracle import dfgan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    depth = {256: 6, 128: 5, 64: 4}[size]
+    g_sd = O.init_generator_state(32, 100, depth=depth)
+    d_sd = O.init_discriminator_state(32, depth=depth)
+    images, sent, noise = O.synthetic_batch(batch, size)
+    go, do = O.AdamState(g_sd, 1e-4), O.AdamState(d_sd, 4e-4)
+    for _ in range(warmup):
+        O.train_step(g_sd, d_sd, go, do, images, sent, noise)
+    best, total = None, 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.train_step(g_sd, d_sd, go, do, images, sent, noise)
+        dt = time.perf_counter() - t0
+        total += dt
+        best = dt if best is None else min(best, dt)
+    return batch * steps / total, cores, total, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = 4
+    t0 = time.perf_counter()
+    ips, cores, total, best = cpu_reference_step(b, args.size, max(1, args.steps), max(0, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": "train images/sec (G+D step, 256x256)", "value": round(ips, 4),
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 * b / ips, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DF-GAN full training iteration {args.size}x{args.size}, n_channels 32, "
+                               f"CPU sample batch {b}", "batch_per_gpu": b},
+        "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} iterations of batch {b} at {args.size}x{args.size} "
+                                   f"({total:.1f} s), oracle/dfgan_oracle.py train_step"},
+        "e2e": {"value": round(ips, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    from gan_codes_b200 import _lib
+    from gan_codes_b200.engine import DFGANTrainer
+    from gan_codes_b200.modules import Discriminator, Generator
+
+    B, S = args.batch, args.size
+    torch.manual_seed(123321)                        # utils.py:27 ; same init on every rank (data parallel)
+    G, D = Generator(32, 100).to(dev), Discriminator(32).to(dev)
+    trainer = DFGANTrainer(G, D, B, world=world)
+    gen = torch.Generator().manual_seed(123321 + 17 * rank)   # every rank draws its own shard
+    images_h = (torch.randn((B, 3, S, S), generator=gen) * 0.5).clamp_(-1, 1).pin_memory()
+    sent_h = (torch.randn((B, 256), generator=gen) * 0.3).pin_memory()
+    noise_h = torch.randn((B, 100), generator=gen).pin_memory()
+    images_d, sent_d, noise_d = images_h.to(dev), sent_h.to(dev), noise_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_dev():
+        trainer.step(images_d, sent_d, noise_d)
+
+    def step_e2e():
+        out = trainer.step(images_h, sent_h, noise_h)
+        return torch.stack([out["d_loss"], out["gp_loss"], out["g_loss"]]).cpu()
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.profile_enable(True)
+    l0 = _lib.launch_count()
+    ms = timed(step_dev, args.steps)
+    launches = _lib.launch_count() - l0
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    clocks = sampler.summary() if sampler else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    losses = {k: float(v) for k, v in trainer.last.items()}
+
+    if rank == 0:
+        hbm, tf_burst, tf_sust, how = _peaks()
+        value = B * world * args.steps / (ms / 1e3)
+        e2e = B * world * args.steps / (ms_e2e / 1e3)
+        dom = max(("conv", "wgrad"), key=lambda k: prof[k]["ms"])
+        p = prof[dom]
+        ach = p["flops"] / (p["ms"] / 1e3) / 1e12 if p["ms"] > 0 else 0.0
+        line = {
+            "metric": "train images/sec (G+D step, 256x256)", "value": round(value, 2), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"DF-GAN full training iteration (D hinge + MA-GP + G, 3x clip+Adam) {S}x{S}, "
+                                   f"n_channels 32, nz 100, cond 256, batch {B}/GPU (BASELINE configs[1])",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations > 2 GB) far exceeds the 126 MB L2; no flush needed",
+                       "pct_of_bf16_peak_algorithmic": round(100 * value / world * GFLOP_PER_IMAGE / 1e3 / tf_sust, 2),
+                       "gflop_per_image_algorithmic": GFLOP_PER_IMAGE, "losses": losses},
+            "e2e": {"value": round(e2e, 2), "unit": "images/s",
+                    "h2d_bytes_per_step": int(images_h.numel() * 4 + sent_h.numel() * 4 + noise_h.numel() * 4),
+                    "d2h_bytes_per_step": 12},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "conv_umma_kernel (dfgan_conv_run)" if dom == "conv" else
+                         "wgrad_umma_kernel (dfgan_wgrad_run)",
+                         "bound": "tensor", "achieved": round(ach, 2), "peak": tf_sust, "unit": "TFLOP/s",
+                         "frac": round(ach / tf_sust, 4), "traffic": None,
+                         "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
+                         "launches_timed": int(p["launches"]), "kernel_ms_per_step": round(p["ms"] / args.steps, 3),
+                         "share_of_step": round(p["ms"] / ms, 4),
+                         "executed_gflop_per_launch_avg": round(p["flops"] / max(p["launches"], 1) / 1e9, 3),
+                         "other_engine": {k: round(v, 3) for k, v in prof["wgrad" if dom == "conv" else "conv"].items()}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ips, cores, total, best = cpu_reference_step(4, S, 3, 1)
+            line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"3 iterations of batch 4 at {S}x{S} ({total:.1f} s) of "
+                                              "oracle/dfgan_oracle.py train_step (fp32, torch CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,6 +83,10 @@ def _declare(l: C.CDLL) -> None:
     l.dfgan_conv_run.restype = C.c_int
     l.dfgan_wgrad_run.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
     l.dfgan_wgrad_run.restype = C.c_int
+    l.dfgan_profile_enable.argtypes = [C.c_int]
+    l.dfgan_profile_enable.restype = None
+    l.dfgan_profile_read.argtypes = [C.POINTER(C.c_double)]
+    l.dfgan_profile_read.restype = C.c_int
     from . import _lib_decl  # noqa: WPS433  (remaining entry points)
     _lib_decl.declare(l)
 
@@ -94,6 +98,17 @@ def check(rc: int, what: str) -> None:
         names = {-1: "invalid argument", -2: "unsupported shape", -3: "driver entry point / tensor map"}
         raise DfganError(f"{what}: {names.get(rc, rc)}")
     raise DfganError(f"{what}: cudaError {rc}")
+
+
+def profile_enable(on: bool) -> None:
+    lib().dfgan_profile_enable(int(on))
+
+
+def profile_read() -> dict:
+    buf = (C.c_double * 8)()
+    check(lib().dfgan_profile_read(buf), "dfgan_profile_read")
+    keys = ("ms", "flops", "bytes", "launches")
+    return {"conv": dict(zip(keys, buf[0:4])), "wgrad": dict(zip(keys, buf[4:8]))}
 
 
 def launch_count() -> int:

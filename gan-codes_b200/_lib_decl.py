@@ -42,4 +42,5 @@ _TABLE: dict = {
 }
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
+           "dfgan_profile_enable", "dfgan_profile_read",
            *_TABLE.keys()]

@@ -238,7 +238,13 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : p.slope);
           }
-          if (p.aux) store_bf16x16(p.aux + o_off + col, v);
+          if (p.aux) {
+            // continue from the stored (bf16) value: what the backward pass reads back is exactly what
+            // the rest of the forward used
+            store_bf16x16(p.aux + o_off + col, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= scale;
           if (p.addend) {
@@ -568,6 +574,16 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   int grid = k.total_tiles;
   const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
   if (grid > cap) grid = cap;
+  // executed work of this launch: real output pixels x Cout x (taps * Cin) MACs; bytes = every source view read
+  // once + weights + the outputs written (the algorithmic minimum for this launch)
+  const double pix = static_cast<double>(d->N) * d->H * d->W;
+  double bytes = 2.0 * d->w_rows * d->Cin;
+  for (int s = 0; s < d->n_src; ++s)
+    bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
+  bytes += pix * d->Cout * 2.0 * ((d->out != nullptr) + (d->aux != nullptr) + (d->out2 != nullptr)) +
+           (d->addend ? pix * d->Cout * 2.0 / (1 << (2 * d->add_shift)) : 0.0) +
+           (d->mask_src ? pix * d->Cout * 2.0 : 0.0) + (d->out_nchw ? pix * d->co_valid * 4.0 : 0.0);
+  ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream);
   cudaError_t e;
   if (BK == 64) {
     e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -662,6 +678,11 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   const size_t smem = static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 1024 + 256;
   int grid = k.total_items;
   if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  const double pix = static_cast<double>(N) * H * W;
+  double bytes = 2.0 * pix * d->Cout + 4.0 * d->n_taps * d->Cin * d->Cout;
+  for (int s = 0; s < d->n_src; ++s)
+    bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
+  ProfileScope prof(1, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream);
   cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -1,6 +1,7 @@
 #include "host_common.h"
 
 #include <mutex>
+#include <vector>
 
 namespace dfgan {
 
@@ -65,9 +66,58 @@ int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int
   return r == CUDA_SUCCESS ? DFGAN_OK : DFGAN_E_DRIVER;
 }
 
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  int engine;
+  double flops, bytes;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+ProfileScope::ProfileScope(int engine, double flops, double bytes, cudaStream_t st_) : slot(-1), st(st_) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{};
+  r.engine = engine, r.flops = flops, r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  slot = static_cast<int>(g_prof.size()) - 1;
+}
+ProfileScope::~ProfileScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].e1, st);
+}
+
 }  // namespace dfgan
 
 extern "C" {
+void dfgan_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(dfgan::g_prof_mu);
+  dfgan::g_prof_on = on != 0;
+}
+// out[engine*4 + {0: ms, 1: flops, 2: bytes, 3: launches}] for engine 0 (conv fprop/dgrad) and 1 (wgrad);
+// synchronises the device, then clears the records.
+int dfgan_profile_read(double* out) {
+  if (!out) return DFGAN_E_ARG;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  std::lock_guard<std::mutex> lk(dfgan::g_prof_mu);
+  for (int i = 0; i < 8; ++i) out[i] = 0.0;
+  for (auto& r : dfgan::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      double* o = out + (r.engine ? 4 : 0);
+      o[0] += ms, o[1] += r.flops, o[2] += r.bytes, o[3] += 1.0;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  dfgan::g_prof.clear();
+  return DFGAN_OK;
+}
 int dfgan_version(void) { return 100; }
 const char* dfgan_arch(void) { return "sm_100a"; }
 uint64_t dfgan_launch_count(void) { return dfgan::g_launches.load(); }

@@ -13,6 +13,15 @@ namespace dfgan {
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional per-launch timing of the two GEMM engines (bench.py's roofline leg): when enabled, every
+// dfgan_conv_run / dfgan_wgrad_run launch is bracketed by a CUDA event pair on its own stream.
+struct ProfileScope {
+  ProfileScope(int engine, double flops, double bytes, cudaStream_t st);
+  ~ProfileScope();
+  int slot;
+  cudaStream_t st;
+};
+
 // cuTensorMapEncodeTiled resolved through the runtime so the library carries no link-time
 // dependency on libcuda (it must load on a CPU-only box for the export test).
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

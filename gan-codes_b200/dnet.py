@@ -114,7 +114,7 @@ def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = 
         saved.append((x, c1, r))
         x = y
     if ctx is not None:
-        ctx.update(xcol=xcol, saved=saved, n=n)
+        ctx.update(xcol=xcol, saved=saved, n=n, emb=x)
     return x
 
 

@@ -1,0 +1,187 @@
+"""Fused training iteration: the step body of DeepFusionGAN.fit (deep_fusion_gan/model.py:173-228) executed as
+three kernel programs over flat parameter / gradient / Adam-moment buffers.
+
+    D step   : G forward (graph kept), D trunk on [real ; fake] as one 2B batch, the three logit heads (real,
+               mismatched, fake) as one (3B-1)-row head call, hinge loss, backward, clip + Adam        (:173-197)
+    MA-GP    : D forward on the real images, first-order sweep for d logits / d(image, sentence), tangent
+               sweep + wgrad against the saved cotangents (App. C-3), clip + Adam                      (:202-210)
+    G step   : twice-updated D on the retained fake images, D dgrad only, G backward, clip + Adam       (:215-228)
+
+Data parallelism: one process per GPU, batch sharded, ONE all-reduce per optimiser step on the
+flat gradient buffer (three per iteration), global-norm clip and Adam on the reduced gradient.  The mismatch
+pairs are formed inside the local shard, exactly like N reference replicas with averaged gradients.
+
+No host synchronisation happens inside `step`; losses are returned as device scalars.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import dnet, gnet
+from . import kernels as K
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+class FlatState:
+    """Parameters of a module re-homed into one flat fp32 buffer (module parameters become views, so
+    state_dict()/load_state_dict() keep working), with same-layout gradient and Adam-moment buffers."""
+
+    def __init__(self, module: nn.Module, lr: float, betas=(0.0, 0.9), eps: float = 1e-8, clip: float = 5.0):
+        named = list(module.named_parameters())
+        dev = named[0][1].device
+        sizes = [((p.numel() + 3) // 4) * 4 for _, p in named]
+        total = sum(sizes)
+        self.flat = torch.zeros(total, device=dev, dtype=F32)
+        self.grad = torch.zeros(total, device=dev, dtype=F32)
+        self.m = torch.zeros(total, device=dev, dtype=F32)
+        self.v = torch.zeros(total, device=dev, dtype=F32)
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[str, torch.Tensor] = {}
+        o = 0
+        with torch.no_grad():
+            for (n, p), s in zip(named, sizes):
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.params[n] = view
+                self.grads[n] = self.grad[o:o + p.numel()].view(p.shape)
+                o += s
+        self.n_real = sum(p.numel() for _, p in named)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.sumsq = torch.zeros(1, device=dev, dtype=F32)
+        self.lr, self.betas, self.eps, self.clip = lr, betas, eps, clip
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+
+    def optimizer_step(self, world: int = 1) -> None:
+        """(all-reduce) -> global L2 norm -> clip -> Adam, all on the flat buffers."""
+        if world > 1:
+            torch.distributed.all_reduce(self.grad)
+        self.sumsq.zero_()
+        K.sqnorm(self.grad, self.sumsq)
+        self.step_count.add_(1)
+        K.adam_step(self.flat, self.grad, self.m, self.v, self.sumsq, self.step_count, lr=self.lr,
+                    gscale=1.0 / world, max_norm=self.clip, b1=self.betas[0], b2=self.betas[1], eps=self.eps)
+
+
+class DFGANTrainer:
+    """step(images, sentence_embeds, noise) == one iteration of the reference's training loop."""
+
+    def __init__(self, generator: nn.Module, discriminator: nn.Module, batch: int, lr_g: float = 1e-4,
+                 lr_d: float = 4e-4, betas=(0.0, 0.9), clip: float = 5.0, world: int = 1):
+        if not next(generator.parameters()).is_cuda:
+            raise RuntimeError("DFGANTrainer: modules must live on a CUDA device (no CPU path)")
+        self.G, self.D = generator, discriminator
+        self.batch, self.world = batch, world
+        self.gs = FlatState(generator, lr_g, betas, clip=clip)
+        self.ds = FlatState(discriminator, lr_d, betas, clip=clip)
+        with torch.no_grad():
+            self.gpk = gnet.GPacked(self.gs.params)
+            self.dpk = dnet.DPacked(self.ds.params)
+            self.mlp = gnet.GMlp(self.gs.params, self.gpk.plan, batch, self.gs.grads)
+        dev = self.gs.flat.device
+        self.ones = torch.ones(batch, device=dev, dtype=F32)
+        self.last: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------ phases
+    def _d_step(self, images, sent, noise):
+        b = self.batch
+        dp, dpk = self.ds.params, self.dpk
+        self.g_ctx: dict = {}
+        fake = gnet.generator_forward(self.gpk, self.gs.params, self.mlp, noise, sent, self.g_ctx)
+        both = torch.cat((images, fake), dim=0)
+        tctx: dict = {}
+        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, both, tctx))         # [2B, C, 4, 4]
+        emb3 = torch.cat((emb[:b], emb[:b - 1], emb[b:]), dim=0)
+        sent3 = torch.cat((sent, sent[1:b], sent), dim=0)
+        hctx: dict = {}
+        lg = dnet.head_forward(dpk, dp, emb3, sent3, hctx)
+        real, mis, fk = lg[:b], lg[b:2 * b - 1], lg[2 * b - 1:]
+        loss = torch.relu(1.0 - real).mean() + 0.5 * (torch.relu(1.0 + fk).mean() + torch.relu(1.0 + mis).mean())
+        g_lg = torch.cat((-(real < 1.0).to(F32) / b, 0.5 * (mis > -1.0).to(F32) / (b - 1),
+                          0.5 * (fk > -1.0).to(F32) / b))
+        self.ds.zero_grad()
+        ge, _ = dnet.head_backward(dpk, dp, hctx, g_lg, self.ds.grads, False)
+        g_emb = torch.cat((ge[:b], ge[2 * b - 1:]), dim=0)
+        g_emb[:b - 1] += ge[b:2 * b - 1]
+        dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_emb), self.ds.grads, False)
+        self.ds.optimizer_step(self.world)
+        dpk.refresh(dp)
+        return loss
+
+    def _gp_step(self, images, sent):
+        b = self.batch
+        dp, dpk = self.ds.params, self.dpk
+        tctx, hctx, cots = {}, {}, {}
+        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, images, tctx))
+        dnet.head_forward(dpk, dp, emb, sent, hctx)
+        g_embed, g_sent = dnet.head_backward(dpk, dp, hctx, None, None, True, cots)
+        gx = dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_embed), None, True, cots)
+        sq = torch.zeros(b, device=gx.device, dtype=F32)
+        K.rowsq(gx, sq)
+        K.rowsq(g_sent, sq)
+        n = torch.sqrt(sq + 1e-8)                                   # deep_fusion_gan/model.py:82
+        nc = torch.clamp(n, 0, 10)                                  # :85
+        loss = 2.0 * torch.mean(nc ** 6)                            # :203
+        coef = (12.0 / b) * n ** 4 * (n <= 10.0).to(F32)            # d loss / d g_b = coef_b * g_b (G11)
+        self.ds.zero_grad()
+        t_emb = dnet.trunk_tangent(dpk, dp, tctx, cots, gx, coef, self.ds.grads)
+        dnet.head_tangent(dpk, dp, hctx, cots, dnet.embeds_to_nchw(t_emb), g_sent, coef, self.ds.grads)
+        self.ds.optimizer_step(self.world)
+        dpk.refresh(dp)
+        return loss
+
+    def _g_step(self, sent):
+        b = self.batch
+        dp, dpk = self.ds.params, self.dpk
+        fake = self.g_ctx["img"]
+        tctx, hctx = {}, {}
+        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, fake, tctx))
+        lg = dnet.head_forward(dpk, dp, emb, sent, hctx)
+        loss = -lg.mean()
+        g_embed, _ = dnet.head_backward(dpk, dp, hctx, self.ones * (-1.0 / b), None, False)
+        g_img = dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_embed), None, True)
+        self.gs.zero_grad()
+        gnet.generator_backward(self.gpk, self.gs.params, self.mlp, self.g_ctx, g_img, self.gs.grads)
+        self.gs.optimizer_step(self.world)
+        self.gpk.refresh(self.gs.params)
+        self.g_ctx = {}
+        return loss
+
+    # ------------------------------------------------------------------------------------ public
+    @torch.no_grad()
+    def step(self, images: torch.Tensor, sentence_embeds: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """One training iteration.  Inputs may live on the host (pinned memory recommended) or on the device:
+        images fp32 [B,3,S,S] in [-1,1], sentence_embeds fp32 [B,256], noise fp32 [B,latent].  Returns the
+        three losses as device scalars (no synchronisation)."""
+        dev = self.gs.flat.device
+        if images.shape[0] != self.batch:
+            raise RuntimeError(f"DFGANTrainer was built for batch {self.batch}, got {images.shape[0]}")
+        images = images.to(dev, F32, non_blocking=True).contiguous()
+        sent = sentence_embeds.to(dev, F32, non_blocking=True).contiguous()
+        noise = noise.to(dev, F32, non_blocking=True).contiguous()
+        d_loss = self._d_step(images, sent, noise)
+        gp_loss = self._gp_step(images, sent)
+        g_loss = self._g_step(sent)
+        self.last = {"d_loss": d_loss, "gp_loss": gp_loss, "g_loss": g_loss}
+        return self.last
+
+    @torch.no_grad()
+    def gp_step(self, images: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
+        """MA-GP discriminator update only (BASELINE config 4)."""
+        dev = self.gs.flat.device
+        return self._gp_step(images.to(dev, F32).contiguous(), sentence_embeds.to(dev, F32).contiguous())
+
+    @torch.no_grad()
+    def sample(self, noise: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
+        """no_grad generator forward (sample.py:13-18, BASELINE config 5)."""
+        dev = self.gs.flat.device
+        n = noise.shape[0]
+        mlp = self.mlp if n == self.batch else gnet.GMlp(self.gs.params, self.gpk.plan, n, None)
+        return gnet.generator_forward(self.gpk, self.gs.params, mlp, noise.to(dev, F32).contiguous(),
+                                      sentence_embeds.to(dev, F32).contiguous(), None)

@@ -26,6 +26,7 @@ from . import dnet, gnet
 from . import kernels as K
 
 F32 = torch.float32
+KEEP_DEBUG = False   # tests set this to keep the last forward's activation dicts on the module (`_debug`)
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -197,6 +198,8 @@ class _EmbedsFn(torch.autograd.Function):
         save: dict = {}
         img = _as_f32(image)
         emb = dnet.trunk_forward(pk, params, img, save)
+        if KEEP_DEBUG:
+            module._debug["trunk"] = save
         ctx.state = (module, pk, params, save, img)
         ctx.save_for_backward(*tensors)
         return dnet.embeds_to_nchw(emb)
@@ -206,7 +209,9 @@ class _EmbedsFn(torch.autograd.Function):
         module, pk, params, save, img = ctx.state
         need_gx = ctx.needs_input_grad[1]
         need_w = any(ctx.needs_input_grad[2:])
-        out = _EmbedsBwdFn.apply(module, pk, save, need_gx, need_w, g_emb, img, *ctx.saved_tensors)
+        # grad mode is on here exactly when the caller asked for create_graph=True (MA-GP first sweep)
+        second = torch.is_grad_enabled()
+        out = _EmbedsBwdFn.apply(module, pk, save, need_gx, need_w, second, g_emb, img, *ctx.saved_tensors)
         return (None, out[0], *out[1:])
 
 
@@ -214,11 +219,10 @@ class _EmbedsBwdFn(torch.autograd.Function):
     """First-order backward of the trunk as a differentiable op: its own backward is the tangent sweep."""
 
     @staticmethod
-    def forward(ctx, module, pk, save, need_gx, need_w, g_emb, img, *tensors):
+    def forward(ctx, module, pk, save, need_gx, need_w, second, g_emb, img, *tensors):
         names = module._trunk_names
         params = dict(zip(names, tensors))
         fg = _FlatGrads(names, list(tensors)) if need_w else None
-        second = torch.is_grad_enabled()
         cots: dict = {} if second else None
         gx = dnet.trunk_backward(pk, params, save, dnet.embeds_to_nhwc(_as_f32(g_emb)),
                                  fg.views if fg else None, need_gx, cots)
@@ -238,7 +242,8 @@ class _EmbedsBwdFn(torch.autograd.Function):
         names = module._trunk_names
         fg = _FlatGrads(names, [params[n] for n in names])   # biases stay exactly zero (gotcha G3)
         t_emb = dnet.trunk_tangent(pk, params, save, cots, _as_f32(gg_x), None, fg.views)
-        return (None, None, None, None, None, dnet.embeds_to_nchw(t_emb), None, *[fg.views[n] for n in names])
+        return (None, None, None, None, None, None, dnet.embeds_to_nchw(t_emb), None,
+                *[fg.views[n] for n in names])
 
 
 class _LogitsFn(torch.autograd.Function):
@@ -248,6 +253,8 @@ class _LogitsFn(torch.autograd.Function):
         pk = module._cache.get(module._all_names, module._all_tensors())
         save: dict = {}
         logits = dnet.head_forward(pk, params, _as_f32(embed), _as_f32(sent), save)
+        if KEEP_DEBUG:
+            module._debug["head"] = save
         ctx.state = (module, pk, params, save)
         ctx.save_for_backward(w0, w2)
         return logits.view(-1, 1, 1, 1)
@@ -255,17 +262,17 @@ class _LogitsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_logits):
         module, pk, params, save = ctx.state
-        out = _LogitsBwdFn.apply(module, pk, save, g_logits, *ctx.saved_tensors)
+        second = torch.is_grad_enabled()
+        out = _LogitsBwdFn.apply(module, pk, save, second, g_logits, *ctx.saved_tensors)
         return (None, *out)
 
 
 class _LogitsBwdFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, pk, save, g_logits, w0, w2):
+    def forward(ctx, module, pk, save, second, g_logits, w0, w2):
         params = {"img_sentence_forward.0.weight": w0, "img_sentence_forward.2.weight": w2}
         names = list(params)
         fg = _FlatGrads(names, [w0, w2])
-        second = torch.is_grad_enabled()
         cots: dict = {} if second else None
         g_embed, g_sent = dnet.head_backward(pk, params, save, _as_f32(g_logits).reshape(-1), fg.views, True, cots)
         ctx.state = (pk, params, save, cots)
@@ -287,7 +294,7 @@ class _LogitsBwdFn(torch.autograd.Function):
         if gg_sent is None:
             gg_sent = torch.zeros(b, dnet.SENT_DIM, device=dev)
         t_logit = dnet.head_tangent(pk, params, save, cots, _as_f32(gg_embed), _as_f32(gg_sent), None, fg.views)
-        return (None, None, None, t_logit.view(-1, 1, 1, 1), fg.views[names[0]], fg.views[names[1]])
+        return (None, None, None, None, t_logit.view(-1, 1, 1, 1), fg.views[names[0]], fg.views[names[1]])
 
 
 class Discriminator(nn.Module):
@@ -305,6 +312,7 @@ class Discriminator(nn.Module):
             nn.LeakyReLU(0.2, inplace=True),
             nn.Conv2d(n_c * 2, 1, 4, 1, 0, bias=False))
         self._cache = _PackCache(dnet.DPacked)
+        self._debug = {}
 
     @property
     def _all_names(self):

@@ -49,7 +49,7 @@ typedef struct dfgan_tap {
  *   v   = acc + bias[co]                      (bias optional)
  *   v   = lrelu_pre ? leaky_relu(v, slope) : v
  *   v  *= (mask_src[n,h,w,co] > 0 ? 1 : slope)                       (mask_src optional, out strides)
- *   aux[n,h,w,co] = bf16(v)                   (aux optional, out strides)
+ *   aux[n,h,w,co] = bf16(v) ; v = bf16(v)     (aux optional, out strides)
  *   v   = v * scale_imm * (scale_dev ? *scale_dev : 1)
  *   v  += add_scale * addend[n, h>>add_shift, w>>add_shift, co]      (addend optional)
  *   out_nchw[n][co][h][w] = tanh_out ? tanh(v) : v   for co < co_valid   (fp32 planar, optional)
@@ -199,6 +199,12 @@ int dfgan_sqnorm(const float* g, int64_t n, float* out, dfgan_stream_t st);
 int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
                     const int* step, float gscale, float max_norm, float lr, float b1, float b2, float eps,
                     dfgan_stream_t st);
+
+/* Per-launch timing of the two GEMM engines with CUDA events on the launching stream (bench.py roofline leg).
+ * dfgan_profile_read: out[e*4 + {0: summed ms, 1: executed FLOPs, 2: algorithmic bytes, 3: launches}], e = 0 for
+ * dfgan_conv_run, 1 for dfgan_wgrad_run; synchronises the device and clears the records. */
+void dfgan_profile_enable(int on);
+int dfgan_profile_read(double* out);
 
 /* Library identification: version = major*10000 + minor*100 + patch; arch string is "sm_100a". */
 int dfgan_version(void);

@@ -49,29 +49,8 @@ def _report(rows, tol):
     return bad == 0
 
 
-@case
-def dfwd():
-    torch, O, g_sd, d_sd, images, sent, noise = _states()
-    from gan_codes_b200 import dnet
-    acts = {}
-    with torch.no_grad():
-        emb_ref = O.discriminator_embeds(d_sd, images, tap=lambda k, v: acts.__setitem__(k, v))
-        log_ref = O.discriminator_logits(d_sd, emb_ref, sent)
-    pk = dnet.DPacked(d_sd)
-    ctx = {}
-    emb = dnet.trunk_forward(pk, d_sd, images, ctx)
-    logits = dnet.head_forward(pk, d_sd, dnet.embeds_to_nchw(emb), sent)
-    torch.cuda.synchronize()
-    rows = []
-    for k, (x, c1, r) in enumerate(ctx["saved"]):
-        p = f"img_forward.{k + 1}"
-        if k == 0:
-            rows.append(("img_forward.0", rel(nchw(x), acts["img_forward.0"])))
-        rows.append((p + ".residual_conv.0 (post-lrelu)", rel(nchw(c1), torch.nn.functional.leaky_relu(acts[p + ".residual_conv.0"], 0.2))))
-        rows.append((p + ".residual_conv.2 (post-lrelu)", rel(nchw(r), torch.nn.functional.leaky_relu(acts[p + ".residual_conv.2"], 0.2))))
-    rows.append(("embeds", rel(nchw(emb), emb_ref)))
-    rows.append(("logits", rel(logits, log_ref.reshape(-1))))
-    return _report(rows, 1e-2)
+def _bf(t):
+    return t.bfloat16().float()
 
 
 def _ref_modules(torch, O, g_sd, d_sd):
@@ -83,35 +62,73 @@ def _ref_modules(torch, O, g_sd, d_sd):
 
 
 @case
-def dbwd():
+def dfwd():
+    """Forward of trunk + head: per-layer against the emulation fed with the pipeline's own inputs (tight), and
+    end-to-end against the free-running emulation and the fp32 oracle (informational)."""
     torch, O, g_sd, d_sd, images, sent, noise = _states()
-    G, D = _ref_modules(torch, O, g_sd, d_sd)
-    fake = (torch.randn_like(images) * 0.5).clamp(-1, 1)
-    dl = {k: v.clone().requires_grad_() for k, v in d_sd.items()}
-    loss_ref = O.d_hinge_loss(dl, images, fake, sent)
-    gref = torch.autograd.grad(loss_ref, list(dl.values()))
-    b = images.shape[0]
-    real_emb = D.build_embeds(images)
-    l_real = torch.relu(1.0 - D.get_logits(real_emb, sent)).mean()
-    l_mis = torch.relu(1.0 + D.get_logits(real_emb[:b - 1], sent[1:b])).mean()
-    l_fake = torch.relu(1.0 + D.get_logits(D.build_embeds(fake), sent)).mean()
-    loss = l_real + (l_fake + l_mis) / 2.0
-    loss.backward()
+    from gan_codes_b200 import dnet
+    from oracle import dfgan_emul as E
+    pk = dnet.DPacked(d_sd)
+    ctx, hctx = {}, {}
+    emb = dnet.trunk_forward(pk, d_sd, images, ctx)
+    logits = dnet.head_forward(pk, d_sd, dnet.embeds_to_nchw(emb), sent, hctx)
     torch.cuda.synchronize()
-    rows = [("d_loss", abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()))]
-    for (k, p), g in zip(D.named_parameters(), gref):
-        rows.append(("grad " + k, rel(p.grad, g)))
-    return _report(rows, 2e-2)
+    q = E.Rounding(True)
+    force = E.force_from_trunk_ctx(ctx, hctx)
+    force["__computed__"] = comp = {}
+    with torch.no_grad():
+        emb_f = E.discriminator_embeds(d_sd, images, q, None, force)
+        log_f = E.discriminator_logits(d_sd, emb_f, sent, q, force)
+        emb_e = E.discriminator_embeds(d_sd, images, q)
+        log_e = E.discriminator_logits(d_sd, emb_e, sent, q)
+        emb_o = O.discriminator_embeds(d_sd, images)
+        log_o = O.discriminator_logits(d_sd, emb_o, sent)
+    rows = [(k, rel(_bf(force[k]), _bf(v))) for k, v in comp.items()]
+    rows.append(("logits (forced inputs)", rel(logits, log_f.reshape(-1))))
+    ok = _report(rows, 2e-3)
+    print("  -- free-running (informational): embeds vs emul %.3e, vs fp32 %.3e; logits vs emul %.3e, vs fp32 %.3e"
+          % (rel(nchw(emb), emb_e), rel(nchw(emb), emb_o), rel(logits, log_e.reshape(-1)), rel(logits, log_o.reshape(-1))))
+    return ok
+
+
+@case
+def dbwd():
+    """First-order backward of head + trunk for L = sum_b c_b * logit_b, against the teacher-forced emulation."""
+    torch, O, g_sd, d_sd, images, sent, noise = _states()
+    from gan_codes_b200 import dnet
+    from gan_codes_b200.modules import _FlatGrads
+    from oracle import dfgan_emul as E
+    pk = dnet.DPacked(d_sd)
+    ctx, hctx = {}, {}
+    emb = dnet.trunk_forward(pk, d_sd, images, ctx)
+    logits = dnet.head_forward(pk, d_sd, dnet.embeds_to_nchw(emb), sent, hctx)
+    cvec = torch.tensor([0.7, -1.3], device="cuda")[:images.shape[0]]
+    names = list(d_sd)
+    fg = _FlatGrads(names, [d_sd[k] for k in names])
+    g_embed, g_sent = dnet.head_backward(pk, d_sd, hctx, cvec, fg.views, True)
+    gx = dnet.trunk_backward(pk, d_sd, ctx, dnet.embeds_to_nhwc(g_embed), fg.views, True)
+    torch.cuda.synchronize()
+    force = E.force_from_trunk_ctx(ctx, hctx)
+    dl = {k: v.clone().requires_grad_() for k, v in d_sd.items()}
+    x = images.clone().requires_grad_()
+    s = sent.clone().requires_grad_()
+    q = E.Rounding(True)
+    lg = E.discriminator_logits(dl, E.discriminator_embeds(dl, x, q, None, force), s, q, force).reshape(-1)
+    gref = torch.autograd.grad((lg * cvec).sum(), [x, s] + list(dl.values()))
+    rows = [("logits", rel(logits, lg)), ("d/d image", rel(gx, gref[0])), ("d/d sentence", rel(g_sent, gref[1]))]
+    for k, g in zip(names, gref[2:]):
+        rows.append(("grad " + k, rel(fg.views[k], g)))
+    return _report(rows, 1e-2)
 
 
 @case
 def gp():
+    """MA-GP through the drop-in modules (autograd.grad(create_graph) + backward) vs the forced emulation."""
     torch, O, g_sd, d_sd, images, sent, noise = _states()
+    import gan_codes_b200.modules as M
+    from oracle import dfgan_emul as E
+    M.KEEP_DEBUG = True
     G, D = _ref_modules(torch, O, g_sd, d_sd)
-    dl = {k: v.clone().requires_grad_() for k, v in d_sd.items()}
-    probe = {}
-    loss_ref = O.magp_loss(dl, images, sent, probe)
-    gref = torch.autograd.grad(loss_ref, list(dl.values()), allow_unused=True)
     x = images.clone().requires_grad_()
     s = sent.clone().requires_grad_()
     logits = D.get_logits(D.build_embeds(x), s)
@@ -121,7 +138,14 @@ def gp():
     loss = 2.0 * torch.mean(n ** 6)
     loss.backward()
     torch.cuda.synchronize()
-    print("  norms ref", probe["gp_n"].tolist(), "ours", n.tolist())
+    force = E.force_from_trunk_ctx(D._debug["trunk"], D._debug["head"])
+    dl = {k: v.clone().requires_grad_() for k, v in d_sd.items()}
+    probe = {}
+    loss_ref = E.magp_loss(dl, images, sent, E.Rounding(True), probe, force)
+    gref = torch.autograd.grad(loss_ref, list(dl.values()), allow_unused=True)
+    p32 = {}
+    loss32 = O.magp_loss(dl, images, sent, p32)
+    print("  norms emul", probe["gp_n"].tolist(), "ours", n.tolist(), "fp32", p32["gp_n"].tolist())
     rows = [("gp_gx", rel(gx, probe["gp_gx"])), ("gp_gs", rel(gs, probe["gp_gs"])),
             ("gp_loss", abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()))]
     for (k, p), gr in zip(D.named_parameters(), gref):
@@ -129,51 +153,133 @@ def gp():
             rows.append(("gp grad (zero) " + k, float(p.grad.abs().max()) if p.grad is not None else 1.0))
         else:
             rows.append(("gp grad " + k, rel(p.grad, gr)))
-    return _report(rows, 3e-2)
+    return _report(rows, 1e-2)
 
 
 @case
 def gfwd():
     torch, O, g_sd, d_sd, images, sent, noise = _states()
     from gan_codes_b200 import gnet
-    acts = {}
-    with torch.no_grad():
-        img_ref = O.generator_forward(g_sd, noise, sent, tap=lambda k, v: acts.__setitem__(k, v))
+    from oracle import dfgan_emul as E
     pk = gnet.GPacked(g_sd)
     mlp = gnet.GMlp(g_sd, pk.plan, noise.shape[0], None)
     ctx = {}
     img = gnet.generator_forward(pk, g_sd, mlp, noise, sent, ctx)
     torch.cuda.synchronize()
     rows = []
-    # gamma/beta tables against the oracle MLPs
-    for (p, fb, m), (o, wdt) in list(mlp.offsets.items())[:8]:
+    for (p, fb, m), (o, wdt) in list(mlp.offsets.items())[:4]:
         rows.append((f"mlp {p}.fusion_block_{fb}.{m}", rel(mlp.tab[:, o:o + wdt], O._mlp(g_sd, f"{p}.fusion_block_{fb}.{m}", sent))))
-    for i, (z_prev, a12, h1, a34) in enumerate(ctx["saved"]):
-        p = pk.plan[i][0]
-        rows.append((p + ".conv_1", rel(nchw(h1), acts[p + ".conv_1"])))
-        if i + 1 < len(ctx["saved"]):
-            rows.append((p + " (block out)", rel(nchw(ctx["saved"][i + 1][0]), acts[p])))
-    rows.append(("res_block_out (block out)", rel(nchw(ctx["z_last"]), acts["res_block_out"])))
-    rows.append(("image", rel(img, img_ref)))
-    return _report(rows, 1e-2)
+    names = [p[0] for p in pk.plan]
+    force = E.force_from_g_ctx(names, ctx)
+    force["__computed__"] = comp = {}
+    q = E.Rounding(True)
+    with torch.no_grad():
+        E.generator_forward(g_sd, noise, sent, q, None, force)
+        img_e = E.generator_forward(g_sd, noise, sent, q)
+        img_o = O.generator_forward(g_sd, noise, sent)
+    rows += [(k, rel(force[k] if k == "img" else _bf(force[k]), v if k == "img" else _bf(v))) for k, v in comp.items()]
+    ok = _report(rows, 2e-3)
+    print("  -- free-running (informational): image vs emul %.3e, vs fp32 %.3e" % (rel(img, img_e), rel(img, img_o)))
+    return ok
 
 
 @case
 def gbwd():
+    """Generator backward for L = <c, image> (random fixed c), against the teacher-forced emulation."""
     torch, O, g_sd, d_sd, images, sent, noise = _states()
-    G, D = _ref_modules(torch, O, g_sd, d_sd)
-    gl = {k: v.clone().requires_grad_() for k, v in g_sd.items()}
-    loss_ref = O.g_hinge_loss(d_sd, O.generator_forward(gl, noise, sent), sent)
-    gref = torch.autograd.grad(loss_ref, list(gl.values()))
-    loss = -D.get_logits(D.build_embeds(G(noise, sent)), sent).mean()
-    loss.backward()
+    from gan_codes_b200 import gnet
+    from gan_codes_b200.modules import _FlatGrads
+    from oracle import dfgan_emul as E
+    pk = gnet.GPacked(g_sd)
+    names_p = list(g_sd)
+    fg = _FlatGrads(names_p, [g_sd[k] for k in names_p])
+    mlp = gnet.GMlp(g_sd, pk.plan, noise.shape[0], fg.views)
+    ctx = {}
+    img = gnet.generator_forward(pk, g_sd, mlp, noise, sent, ctx)
+    cimg = torch.randn_like(img) * 0.01
+    gnet.generator_backward(pk, g_sd, mlp, ctx, cimg, fg.views)
     torch.cuda.synchronize()
-    rows = [("g_loss", abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()))]
-    for (k, p), g in zip(G.named_parameters(), gref):
-        rows.append(("grad " + k, rel(p.grad, g)))
-    worst = sorted(rows, key=lambda r: -r[1])[:25]
-    ok = _report(worst, 3e-2)
-    print(f"  ({len(rows)} tensors, worst 25 shown)")
+    force = E.force_from_g_ctx([p[0] for p in pk.plan], ctx)
+    gl = {k: v.clone().requires_grad_() for k, v in g_sd.items()}
+    img_e = E.generator_forward(gl, noise, sent, E.Rounding(True), None, force)
+    gref = torch.autograd.grad((img_e * cimg).sum(), list(gl.values()))
+    rows = [("grad " + k, rel(fg.views[k], g)) for k, g in zip(names_p, gref)]
+    worst = sorted(rows, key=lambda r: -r[1])[:30]
+    ok = _report(worst, 1e-2)
+    print(f"  ({len(rows)} tensors, worst 30 shown; median {sorted(r[1] for r in rows)[len(rows) // 2]:.3e})")
+    return ok
+
+
+@case
+def step_modules():
+    """Full training iteration through the drop-in modules + torch.optim.Adam vs the fp32 oracle step (losses)."""
+    torch, O, g_sd, d_sd, images, sent, noise = _states(batch=4, ws=1.0)
+    G, D = _ref_modules(torch, O, g_sd, d_sd)
+    g_opt = torch.optim.Adam(G.parameters(), lr=1e-4, betas=(0.0, 0.9))
+    d_opt = torch.optim.Adam(D.parameters(), lr=4e-4, betas=(0.0, 0.9))
+    og, od = O.AdamState(g_sd, 1e-4), O.AdamState(d_sd, 4e-4)
+    ok = True
+    for it in range(2):
+        ref = O.train_step(g_sd, d_sd, og, od, images, sent, noise)
+        b = images.shape[0]
+        real_emb = D.build_embeds(images)
+        l_real = torch.relu(1.0 - D.get_logits(real_emb, sent)).mean()
+        l_mis = torch.relu(1.0 + D.get_logits(real_emb[:b - 1], sent[1:b])).mean()
+        fake = G(noise, sent)
+        l_fake = torch.relu(1.0 + D.get_logits(D.build_embeds(fake.detach()), sent)).mean()
+        d_loss = l_real + (l_fake + l_mis) / 2.0
+        d_opt.zero_grad(); g_opt.zero_grad()
+        d_loss.backward()
+        torch.nn.utils.clip_grad_norm_(D.parameters(), 5.0)
+        d_opt.step()
+        x = images.data.requires_grad_()
+        s = sent.data.requires_grad_()
+        lg = D.get_logits(D.build_embeds(x), s)
+        grads = torch.autograd.grad(lg, (x, s), torch.ones_like(lg), retain_graph=True, create_graph=True)
+        gcat = torch.cat((grads[0].reshape(b, -1), grads[1].reshape(b, -1)), dim=1)
+        gp = 2.0 * torch.mean(torch.clamp(torch.sqrt(torch.sum(gcat ** 2, dim=1) + 1e-8), 0, 10) ** 6)
+        d_opt.zero_grad(); g_opt.zero_grad()
+        gp.backward()
+        torch.nn.utils.clip_grad_norm_(D.parameters(), 5.0)
+        d_opt.step()
+        g_loss = -D.get_logits(D.build_embeds(fake), sent).mean()
+        d_opt.zero_grad(); g_opt.zero_grad()
+        g_loss.backward()
+        torch.nn.utils.clip_grad_norm_(G.parameters(), 5.0)
+        g_opt.step()
+        torch.cuda.synchronize()
+        rows = [(f"it{it} d_loss", abs(d_loss.item() - ref["d"].item()) / abs(ref["d"].item())),
+                (f"it{it} gp_loss", abs(gp.item() - ref["gp"].item()) / abs(ref["gp"].item())),
+                (f"it{it} g_loss", abs(g_loss.item() - ref["g"].item()) / abs(ref["g"].item()))]
+        print("  ours d %.5f gp %.5f g %.5f | oracle d %.5f gp %.5f g %.5f" % (
+            d_loss.item(), gp.item(), g_loss.item(), ref["d"].item(), ref["gp"].item(), ref["g"].item()))
+        ok &= _report(rows, 5e-2)
+    return ok
+
+
+@case
+def engine():
+    """DFGANTrainer.step (fused engine) vs the fp32 oracle step: losses over 3 iterations, then parameters."""
+    torch, O, g_sd, d_sd, images, sent, noise = _states(batch=4, ws=1.0)
+    from gan_codes_b200.engine import DFGANTrainer
+    G, D = _ref_modules(torch, O, g_sd, d_sd)
+    tr = DFGANTrainer(G, D, 4)
+    og, od = O.AdamState(g_sd, 1e-4), O.AdamState(d_sd, 4e-4)
+    ok = True
+    for it in range(3):
+        ref = O.train_step(g_sd, d_sd, og, od, images, sent, noise)
+        out = tr.step(images, sent, noise)
+        torch.cuda.synchronize()
+        print("  ours d %.5f gp %.6g g %.5f | oracle d %.5f gp %.6g g %.5f" % (
+            out["d_loss"].item(), out["gp_loss"].item(), out["g_loss"].item(), ref["d"].item(), ref["gp"].item(),
+            ref["g"].item()))
+        rows = [(f"it{it} {k}", abs(out[k + "_loss"].item() - ref[k].item()) / (abs(ref[k].item()) + 1e-3))
+                for k in ("d", "gp", "g")]
+        ok &= _report(rows, 5e-2)
+    dsd, gsd = D.state_dict(), G.state_dict()
+    rows = [("param D " + k, rel(dsd[k], v)) for k, v in d_sd.items()][:8]
+    rows += [("param G " + k, rel(gsd[k], v)) for k, v in g_sd.items() if "conv" in k][:8]
+    ok &= _report(rows, 2e-2)
     return ok
 
 
