@@ -13,6 +13,8 @@ class LinearItem(C.Structure):
 
 
 def declare(l: C.CDLL) -> None:
+    l.dfgan_pack_entry_size.argtypes = []
+    l.dfgan_pack_entry_size.restype = C.c_int
     for name, argtypes in _TABLE.items():
         fn = getattr(l, name)   # AttributeError = header and library disagree: fail loudly
         fn.argtypes = argtypes
@@ -36,11 +38,13 @@ _TABLE: dict = {
     "dfgan_head_out_bwd": [P, P, P, P, P, P, I, I, P],
     "dfgan_linear_batched": [P, I, I, I, I, I, P],
     "dfgan_pack_weights": [P, P, I, I, I, I, I, I, I, P, F, P],
+    "dfgan_pack_entry_fill": [P, P, P, I, I, I, I, I, I, I, P, F, I],
+    "dfgan_pack_batched": [P, I, I, P],
     "dfgan_unfold_subpixel_wgrad": [P, P, I, I, P],
     "dfgan_sqnorm": [P, L, P, P],
     "dfgan_adam_step": [P, P, P, P, L, P, P, F, F, F, F, F, F, P],
 }
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
-           "dfgan_profile_enable", "dfgan_profile_read",
+           "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size",
            *_TABLE.keys()]

@@ -515,13 +515,22 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     return DFGAN_E_ARG;
   if (d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1) return DFGAN_E_SHAPE;
   const int BK = (d->Cin % 64 == 0) ? 64 : 32;
-  int n_tile = d->n_tile_hint > 0 ? d->n_tile_hint : (d->Cout <= 256 ? d->Cout : 256);
-  if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return DFGAN_E_SHAPE;
-
   ConvK k{};
   ConvMaps maps{};
   brick_geometry(d->W, d->H, k.lbw, k.lbh);
   const int BW = 1 << k.lbw, BH = 1 << k.lbh, BN = 128 / (BW * BH);
+  int n_tile = d->n_tile_hint;
+  if (n_tile <= 0) {
+    // widest N tile that still gives every SM a tile: small grids (low resolutions) trade A-tile re-reads
+    // from L2 for occupancy of the 148 SMs
+    const long long m_tiles = static_cast<long long>((d->W + BW - 1) / BW) * ((d->H + BH - 1) / BH) *
+                              ((d->N + BN - 1) / BN);
+    n_tile = d->Cout <= 256 ? d->Cout : 256;
+    while (n_tile > 64 && n_tile % 32 == 0 && d->Cout % (n_tile / 2) == 0 &&
+           m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
+      n_tile /= 2;
+  }
+  if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return DFGAN_E_SHAPE;
   k.tiles_w = (d->W + BW - 1) / BW;
   k.tiles_h = (d->H + BH - 1) / BH;
   k.tiles_n = (d->N + BN - 1) / BN;

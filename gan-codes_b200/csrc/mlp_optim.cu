@@ -142,6 +142,34 @@ __global__ void pack_kernel(const __grid_constant__ PackP p) {
   }
   p.out[i] = __float2bfloat16_rn(v * p.scale);
 }
+// All weight tensors of a network in one launch: entries[e] = PackP + first block; a block finds its entry by
+// scanning the (<= 128-entry) table.
+struct PackEntry {
+  PackP p;
+  int block_start;
+};
+__global__ void pack_batched_kernel(const PackEntry* __restrict__ entries, int n_entries) {
+  int e = 0;
+  while (e + 1 < n_entries && static_cast<int>(blockIdx.x) >= entries[e + 1].block_start) ++e;
+  const PackP& p = entries[e].p;
+  const long long total = static_cast<long long>(p.n_slots) * p.rows_pad * p.cols_pad;
+  const long long i = (blockIdx.x - entries[e].block_start) * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int col = i % p.cols_pad;
+  const long long t = i / p.cols_pad;
+  const int row = t % p.rows_pad;
+  const int slot = t / p.rows_pad;
+  const int co = p.transpose ? col : row, ci = p.transpose ? row : col;
+  float v = 0.f;
+  if (co < p.Co && ci < p.Ci) {
+    const float* src = p.w + (static_cast<long long>(co) * p.Ci + ci) * p.KK;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (p.taps[slot][j] >= 0) v += __ldg(src + p.taps[slot][j]);
+  }
+  p.out[i] = __float2bfloat16_rn(v * p.scale);
+}
+
 // dw[co][ci][r*3+s] += sum_{a,c} folded[(a*2+c)*4 + dyi_a(r)*2 + dxi_c(s)][co][ci]   (sub-pixel un-fold)
 __global__ void unfold_kernel(const float* __restrict__ folded, float* __restrict__ dw, int Co, int Ci) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -248,6 +276,35 @@ int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int tr
     for (int j = 0; j < 4; ++j) p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
   const long long total = static_cast<long long>(n_slots) * rows_pad * cols_pad;
   pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, STREAM(st)>>>(p);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_pack_entry_size(void) { return static_cast<int>(sizeof(PackEntry)); }
+
+/* Fills one host-side table entry (entry_out points at dfgan_pack_entry_size() bytes); returns the number of
+ * 256-thread blocks the entry needs, or a negative error.  block_start is the running block offset. */
+int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, int Ci, int KK, int transpose,
+                          int rows_pad, int cols_pad, int n_slots, const int8_t* slot_taps, float scale,
+                          int block_start) {
+  if (!entry_out || !w || !out || !slot_taps || n_slots < 1 || n_slots > 16) return DFGAN_E_ARG;
+  if (rows_pad < (transpose ? Ci : Co) || cols_pad < (transpose ? Co : Ci)) return DFGAN_E_SHAPE;
+  PackEntry e{};
+  e.p.w = w, e.p.out = static_cast<__nv_bfloat16*>(out);
+  e.p.Co = Co, e.p.Ci = Ci, e.p.KK = KK, e.p.transpose = transpose;
+  e.p.rows_pad = rows_pad, e.p.cols_pad = cols_pad, e.p.n_slots = n_slots, e.p.scale = scale;
+  for (int s = 0; s < 16; ++s)
+    for (int j = 0; j < 4; ++j) e.p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
+  e.block_start = block_start;
+  *static_cast<PackEntry*>(entry_out) = e;
+  const long long total = static_cast<long long>(n_slots) * rows_pad * cols_pad;
+  return static_cast<int>((total + 255) / 256);
+}
+
+int dfgan_pack_batched(const void* entries_dev, int n_entries, int total_blocks, dfgan_stream_t st) {
+  if (!entries_dev || n_entries < 1 || total_blocks < 1) return DFGAN_E_ARG;
+  pack_batched_kernel<<<total_blocks, 256, 0, STREAM(st)>>>(static_cast<const PackEntry*>(entries_dev), n_entries);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;

@@ -55,22 +55,33 @@ class DPacked:
         wh = params["img_sentence_forward.0.weight"]
         self.ch, self.ccat = wh.shape[0], wh.shape[1]
         self.wh_f, self.wh_d = e(9 * self.ch, self.ccat), e(9 * self.ccat, self.ch)
+        self._ptrs = None
         self.refresh(params)
 
-    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
-        K.pack_weights(params["img_forward.0.weight"], self.w0_f, as_matrix=True, cols_pad=32)
-        K.pack_weights(params["img_forward.0.weight"], self.w0_d, transpose=True, rows_pad=16)
+    def _build(self, params: Dict[str, torch.Tensor]) -> None:
+        pp = K.PackPlan(params["img_forward.0.weight"].device)
+        pp.add(params["img_forward.0.weight"], self.w0_f, as_matrix=True, cols_pad=32)
+        pp.add(params["img_forward.0.weight"], self.w0_d, transpose=True, rows_pad=16)
         for (p, cin, cout, sc), b in zip(self.plan, self.blocks):
             w4, w3 = params[p + ".residual_conv.0.weight"], params[p + ".residual_conv.2.weight"]
-            K.pack_weights(w4, b["w4_f"])
-            K.pack_weights(w4, b["w4_d"], transpose=True)
-            K.pack_weights(w3, b["w3_f"])
-            K.pack_weights(w3, b["w3_d"], transpose=True)
+            pp.add(w4, b["w4_f"])
+            pp.add(w4, b["w4_d"], transpose=True)
+            pp.add(w3, b["w3_f"])
+            pp.add(w3, b["w3_d"], transpose=True)
             if sc:
-                K.pack_weights(params[p + ".scale_conv.weight"], b["ws_f"], scale=0.25)
-                K.pack_weights(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)
-        K.pack_weights(params["img_sentence_forward.0.weight"], self.wh_f)
-        K.pack_weights(params["img_sentence_forward.0.weight"], self.wh_d, transpose=True)
+                pp.add(params[p + ".scale_conv.weight"], b["ws_f"], scale=0.25)
+                pp.add(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)
+        pp.add(params["img_sentence_forward.0.weight"], self.wh_f)
+        pp.add(params["img_sentence_forward.0.weight"], self.wh_d, transpose=True)
+        self._pp = pp
+
+    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
+        """Re-pack every GEMM operand from the fp32 master weights: one kernel launch."""
+        ptrs = tuple(t.data_ptr() for t in params.values())
+        if ptrs != self._ptrs:
+            self._build(params)
+            self._ptrs = ptrs
+        self._pp.run()
 
 
 def _oihw_strides(w: torch.Tensor) -> tuple:

@@ -15,6 +15,7 @@ No host synchronisation happens inside `step`; losses are returned as device sca
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -73,7 +74,8 @@ class DFGANTrainer:
     """step(images, sentence_embeds, noise) == one iteration of the reference's training loop."""
 
     def __init__(self, generator: nn.Module, discriminator: nn.Module, batch: int, lr_g: float = 1e-4,
-                 lr_d: float = 4e-4, betas=(0.0, 0.9), clip: float = 5.0, world: int = 1):
+                 lr_d: float = 4e-4, betas=(0.0, 0.9), clip: float = 5.0, world: int = 1,
+                 use_graph: Optional[bool] = None):
         if not next(generator.parameters()).is_cuda:
             raise RuntimeError("DFGANTrainer: modules must live on a CUDA device (no CPU path)")
         self.G, self.D = generator, discriminator
@@ -87,6 +89,15 @@ class DFGANTrainer:
         dev = self.gs.flat.device
         self.ones = torch.ones(batch, device=dev, dtype=F32)
         self.last: Dict[str, torch.Tensor] = {}
+        # The iteration is ~400 kernel launches; replaying it as ONE CUDA graph removes the host launch cost
+        # (the eager path is host-bound).  Inputs are staged into static buffers, two eager iterations warm up
+        # every lazily built table, the third call captures.
+        if use_graph is None:
+            use_graph = os.environ.get("DFGAN_NO_GRAPH", "0") != "1"
+        self.use_graph = use_graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._eager_calls = 0
+        self._in = None
 
     # ------------------------------------------------------------------------------------ phases
     def _d_step(self, images, sent, noise):
@@ -154,21 +165,39 @@ class DFGANTrainer:
         return loss
 
     # ------------------------------------------------------------------------------------ public
+    def _body(self, images, sent, noise) -> Dict[str, torch.Tensor]:
+        d_loss = self._d_step(images, sent, noise)
+        gp_loss = self._gp_step(images, sent)
+        g_loss = self._g_step(sent)
+        return {"d_loss": d_loss, "gp_loss": gp_loss, "g_loss": g_loss}
+
     @torch.no_grad()
     def step(self, images: torch.Tensor, sentence_embeds: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One training iteration.  Inputs may live on the host (pinned memory recommended) or on the device:
         images fp32 [B,3,S,S] in [-1,1], sentence_embeds fp32 [B,256], noise fp32 [B,latent].  Returns the
-        three losses as device scalars (no synchronisation)."""
+        three losses as device scalars (no synchronisation; with graphs the tensors are overwritten by the
+        next call)."""
         dev = self.gs.flat.device
         if images.shape[0] != self.batch:
             raise RuntimeError(f"DFGANTrainer was built for batch {self.batch}, got {images.shape[0]}")
-        images = images.to(dev, F32, non_blocking=True).contiguous()
-        sent = sentence_embeds.to(dev, F32, non_blocking=True).contiguous()
-        noise = noise.to(dev, F32, non_blocking=True).contiguous()
-        d_loss = self._d_step(images, sent, noise)
-        gp_loss = self._gp_step(images, sent)
-        g_loss = self._g_step(sent)
-        self.last = {"d_loss": d_loss, "gp_loss": gp_loss, "g_loss": g_loss}
+        if self._in is None:
+            self._in = (torch.empty(images.shape, device=dev, dtype=F32),
+                        torch.empty(sentence_embeds.shape, device=dev, dtype=F32),
+                        torch.empty(noise.shape, device=dev, dtype=F32))
+        for dst, src in zip(self._in, (images, sentence_embeds, noise)):
+            dst.copy_(src, non_blocking=True)
+        if not self.use_graph or self._eager_calls < 2:
+            self._eager_calls += 1
+            self.last = self._body(*self._in)
+            return self.last
+        if self._graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self._body(*self._in)
+            self._graph = g
+        self._graph.replay()
+        self.last = self._graph_out
         return self.last
 
     @torch.no_grad()

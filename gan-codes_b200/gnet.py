@@ -56,21 +56,32 @@ class GPacked:
         self.c_last = self.plan[-1][2]
         self.wo_f, self.wo_d = e(9 * 16, self.c_last), e(9 * self.c_last, 32)
         self.bo16 = torch.zeros(16, device=dev, dtype=F32)
+        self._ptrs = None
         self.refresh(params)
 
-    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
+    def _build(self, params: Dict[str, torch.Tensor]) -> None:
+        pp = K.PackPlan(params["linear_in.weight"].device)
         slots = co.subpixel_slots()
         for i, ((p, c1, c2, sc), b) in enumerate(zip(self.plan, self.blocks)):
             w1, w2 = params[p + ".conv_1.weight"], params[p + ".conv_2.weight"]
-            K.pack_weights(w1, b["w1_f"], slots=None if i == 0 else slots)
-            K.pack_weights(w1, b["w1_d"], transpose=True, slots=None if i == 0 else slots)
-            K.pack_weights(w2, b["w2_f"])
-            K.pack_weights(w2, b["w2_d"], transpose=True)
+            pp.add(w1, b["w1_f"], slots=None if i == 0 else slots)
+            pp.add(w1, b["w1_d"], transpose=True, slots=None if i == 0 else slots)
+            pp.add(w2, b["w2_f"])
+            pp.add(w2, b["w2_d"], transpose=True)
             if sc:
-                K.pack_weights(params[p + ".scale_conv.weight"], b["ws_f"])
-                K.pack_weights(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)
-        K.pack_weights(params["conv_out.1.weight"], self.wo_f, rows_pad=16)
-        K.pack_weights(params["conv_out.1.weight"], self.wo_d, transpose=True, cols_pad=32)
+                pp.add(params[p + ".scale_conv.weight"], b["ws_f"])
+                pp.add(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)
+        pp.add(params["conv_out.1.weight"], self.wo_f, rows_pad=16)
+        pp.add(params["conv_out.1.weight"], self.wo_d, transpose=True, cols_pad=32)
+        self._pp = pp
+
+    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
+        """Re-pack every GEMM operand from the fp32 master weights: one kernel launch (+ the padded bias)."""
+        ptrs = tuple(t.data_ptr() for t in params.values())
+        if ptrs != self._ptrs:
+            self._build(params)
+            self._ptrs = ptrs
+        self._pp.run()
         self.bo16[:3].copy_(params["conv_out.1.bias"])
 
 

@@ -181,6 +181,41 @@ def pack_weights(w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None,
           C.cast(flat, C.c_void_p), scale, _s())
 
 
+class PackPlan:
+    """All weight re-packs of a network as ONE launch: `add` mirrors pack_weights and records a table entry,
+    `run` replays the table (built on first use; tensors must stay in place)."""
+
+    def __init__(self, device):
+        self.device, self.entries, self.blocks, self.dev = device, [], 0, None
+        self.esize = _lib.lib().dfgan_pack_entry_size()
+
+    def add(self, w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False):
+        assert self.dev is None and w.dtype == F32 and w.is_contiguous() and out.dtype == BF16 and out.is_contiguous()
+        co, ci, kh, kw = w.shape
+        if as_matrix:
+            ci, kh, kw = ci * kh * kw, 1, 1
+        if slots is None:
+            slots = [[t] for t in range(kh * kw)]
+        rows, cols = (ci, co) if transpose else (co, ci)
+        rows_pad, cols_pad = rows_pad or rows, cols_pad or cols
+        assert out.numel() == len(slots) * rows_pad * cols_pad
+        flat = (C.c_int8 * (len(slots) * 4))(*[(s[j] if j < len(s) else -1) for s in slots for j in range(4)])
+        buf = (C.c_uint8 * self.esize)()
+        nb = _lib.lib().dfgan_pack_entry_fill(C.cast(buf, C.c_void_p), _p(w), _p(out), co, ci, kh * kw,
+                                              int(transpose), rows_pad, cols_pad, len(slots),
+                                              C.cast(flat, C.c_void_p), scale, self.blocks)
+        if nb < 0:
+            _lib.check(nb, "dfgan_pack_entry_fill")
+        self.entries.append(bytes(buf))
+        self.blocks += nb
+
+    def run(self):
+        if self.dev is None:
+            raw = torch.frombuffer(bytearray(b"".join(self.entries)), dtype=torch.uint8)
+            self.dev = raw.to(self.device)
+        _call("dfgan_pack_batched", self.dev.data_ptr(), len(self.entries), self.blocks, _s())
+
+
 def unfold_subpixel_wgrad(folded, dw):
     co, ci = dw.shape[0], dw.shape[1]
     assert folded.dtype == F32 and folded.numel() == 16 * co * ci and dw.dtype == F32 and dw.is_contiguous()

@@ -190,6 +190,14 @@ int dfgan_linear_batched(const dfgan_linear_item* items_dev, int n_items, int B,
  * taps slot_taps[s][0..3] (-1 = unused; HOST array); transpose 0: rows=co, cols=ci; 1: rows=ci, cols=co. */
 int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int transpose, int rows_pad,
                        int cols_pad, int n_slots, const int8_t* slot_taps, float scale, dfgan_stream_t st);
+/* The same for every weight tensor of a network in ONE launch: a host table of dfgan_pack_entry_size()-byte
+ * entries is filled with dfgan_pack_entry_fill (returns the entry's block count; block_start = running sum),
+ * copied to the device once, and replayed after every optimiser step by dfgan_pack_batched. */
+int dfgan_pack_entry_size(void);
+int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, int Ci, int KK, int transpose,
+                          int rows_pad, int cols_pad, int n_slots, const int8_t* slot_taps, float scale,
+                          int block_start);
+int dfgan_pack_batched(const void* entries_dev, int n_entries, int total_blocks, dfgan_stream_t st);
 /* dw[co][ci][3][3] += un-folded sub-pixel weight gradient folded[16][co][ci]. */
 int dfgan_unfold_subpixel_wgrad(const float* folded, float* dw, int Co, int Ci, dfgan_stream_t st);
 
