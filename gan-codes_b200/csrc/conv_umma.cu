@@ -11,6 +11,8 @@
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
+#include <cstdlib>
+
 namespace dfgan {
 
 constexpr int kConvThreads = 192;
@@ -91,6 +93,68 @@ __device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* src, float* v)
 }
 __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+// One 16-column chunk of the fused epilogue for one output pixel (see dfgan_conv_run in the header).
+__device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], int col, int n, int h, int w,
+                                               long long o_off, long long a_off, float scale) {
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + col + i);
+    }
+    if (p.lrelu_pre) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+    }
+    if (p.mask_src) {
+      float m[16];
+      load_bf16x16(p.mask_src + o_off + col, m);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : p.slope);
+    }
+    if (p.aux) {
+      // continue from the stored (bf16) value: what the backward pass reads back is exactly what
+      // the rest of the forward used
+      store_bf16x16(p.aux + o_off + col, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= scale;
+    if (p.addend) {
+      float a[16];
+      load_bf16x16(p.addend + a_off + col, a);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += p.add_scale * a[i];
+    }
+    if (p.out_nchw) {
+      // image boundary: fp32 planar store, lanes of a warp hold consecutive w -> coalesced
+      const long long hw = static_cast<long long>(p.H) * p.W;
+      float* dst = p.out_nchw + (static_cast<long long>(n) * p.co_valid) * hw +
+                   static_cast<long long>(h) * p.W + w;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (col + i < p.co_valid) dst[(col + i) * hw] = p.tanh_out ? tanhf(v[i]) : v[i];
+      }
+    }
+    if (p.out) store_bf16x16(p.out + o_off + col, v);
+    if (p.post_mode) {
+      // the follow-up pointwise chain is evaluated on the bf16-rounded value that `out`/`aux`
+      // hold, so a backward pass that recomputes it from the stored tensor sees identical masks
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+      if (p.post_mode == 2) {
+        const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float u = lrelu(fmaf(__ldg(p.tab_ga + t_off + i), v[i], __ldg(p.tab_ba + t_off + i)), p.slope);
+          v[i] = fmaf(__ldg(p.tab_gb + t_off + i), u, __ldg(p.tab_bb + t_off + i));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+      store_bf16x16(p.out2 + o_off + col, v);
+    }
 }
 
 template <int BK>
@@ -223,65 +287,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         float v[16];
         tmem_ld16(taddr + c, v);
         const int col = nt * p.n_tile + c;
-        if (valid && col < p.Cout) {
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + col + i);
-          }
-          if (p.lrelu_pre) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
-          }
-          if (p.mask_src) {
-            float m[16];
-            load_bf16x16(p.mask_src + o_off + col, m);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : p.slope);
-          }
-          if (p.aux) {
-            // continue from the stored (bf16) value: what the backward pass reads back is exactly what
-            // the rest of the forward used
-            store_bf16x16(p.aux + o_off + col, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= scale;
-          if (p.addend) {
-            float a[16];
-            load_bf16x16(p.addend + a_off + col, a);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += p.add_scale * a[i];
-          }
-          if (p.out_nchw) {
-            // image boundary: fp32 planar store, lanes of a warp hold consecutive w -> coalesced
-            const long long hw = static_cast<long long>(p.H) * p.W;
-            float* dst = p.out_nchw + (static_cast<long long>(n) * p.co_valid) * hw +
-                         static_cast<long long>(h) * p.W + w;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (col + i < p.co_valid) dst[(col + i) * hw] = p.tanh_out ? tanhf(v[i]) : v[i];
-            }
-          }
-          if (p.out) store_bf16x16(p.out + o_off + col, v);
-          if (p.post_mode) {
-            // the follow-up pointwise chain is evaluated on the bf16-rounded value that `out`/`aux`
-            // hold, so a backward pass that recomputes it from the stored tensor sees identical masks
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
-            if (p.post_mode == 2) {
-              const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float u = lrelu(fmaf(__ldg(p.tab_ga + t_off + i), v[i], __ldg(p.tab_ba + t_off + i)), p.slope);
-                v[i] = fmaf(__ldg(p.tab_gb + t_off + i), u, __ldg(p.tab_bb + t_off + i));
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
-            store_bf16x16(p.out2 + o_off + col, v);
-          }
-        }
+        if (valid && col < p.Cout) epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale);
       }
       tc_fence_before();
       __syncwarp();
@@ -483,6 +489,228 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+constexpr size_t kSmemBudget = 200 * 1024;
+
+// ---------------------------------------------------------------------------------------------
+// Halo variant for the high-resolution, narrow layers (C_in <= 64, where the tap-list kernel above is bound
+// by re-reading the A tile from L2 once per filter tap).  An M tile is a 16(h) x 8(w) pixel brick; for every
+// source view ONE 5-D TMA load brings the brick plus its halo into shared memory as
+// [channel slice of 8][h][w][8 ch] -- the canonical no-swizzle K-major layout, in which a filter tap (dy,dx)
+// is just a different start address (SBO = one halo row, LBO = one channel slice).  All taps of the packed
+// weight matrix stay resident in shared memory for the life of the CTA.  Per 128 output pixels the kernel
+// moves (16+2)(8+2) * C_in * 2 bytes instead of taps * 128 * (C_in + n_tile) * 2.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 two epilogue warpgroups alternating tiles over
+// up to four TMEM accumulator stages (the epilogue, not the MMA, bounds these layers).
+constexpr int kHaloThreads = 320;
+
+struct HaloK {
+  int dy_min[DFGAN_MAX_SRC], dx_min[DFGAN_MAX_SRC];
+  int n_src, hal_w, hal_h;
+  uint32_t a_src_bytes;   // one source's halo tile, padded to 128 B
+  uint32_t kslice_bytes;  // hal_h * hal_w * 16
+  uint32_t b_tap_bytes;   // n_tile * C_in * 2
+  int n_acc;              // TMEM accumulator stages (2 or 4)
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+    conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p,
+                     const __grid_constant__ HaloK hp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr int kAStages = 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_taps) * hp.b_tap_bytes;
+  const uint32_t a_stage_bytes = static_cast<uint32_t>(hp.n_src) * hp.a_src_bytes;
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kAStages * a_stage_bytes);
+  uint64_t* full = bars;               // [2]
+  uint64_t* empty = bars + 2;          // [2]
+  uint64_t* tfull = bars + 4;          // [4]
+  uint64_t* tempty = bars + 8;         // [4]
+  uint64_t* bfull = bars + 12;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = hp.n_acc * p.n_tile <= 32 ? 32u : (hp.n_acc * p.n_tile <= 64 ? 64u :
+                             (hp.n_acc * p.n_tile <= 128 ? 128u : (hp.n_acc * p.n_tile <= 256 ? 256u : 512u)));
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DFGAN_MAX_SRC; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(bfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bfull, b_bytes);
+      for (int t = 0; t < p.n_taps; ++t)
+        tma_load_2d(sB + static_cast<size_t>(t) * hp.b_tap_bytes, &maps.b, bfull, 0, p.tap_wrow[t]);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = static_cast<uint32_t>(hp.n_src) * hp.kslice_bytes * (CIN / 8);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int r = tile / p.tiles_w;
+        const int th = r % p.tiles_h;
+        const int n = r / p.tiles_h;
+        wait_bounded(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], tx);
+        uint8_t* dst = sA + static_cast<size_t>(stage) * a_stage_bytes;
+        for (int s = 0; s < hp.n_src; ++s)
+          tma_load_5d(dst + static_cast<size_t>(s) * hp.a_src_bytes, &maps.a[s], &full[stage], 0,
+                      (tw << 3) + hp.dx_min[s], (th << 4) + hp.dy_min[s], 0, n);
+        if (++stage == kAStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t swz_b = (CIN == 64) ? SWZ_128B : SWZ_64B;
+    constexpr uint32_t sbo_b = 8u * CIN * 2u;
+    const uint32_t sbo_a = static_cast<uint32_t>(hp.hal_w) * 16u;
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, aphase = 0;
+    wait_bounded(bfull, 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      wait_bounded(&tempty[acc], aphase ^ 1);
+      wait_bounded(&full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * a_stage_bytes);
+        const uint32_t b_base = smem_u32(sB);
+        for (int t = 0; t < p.n_taps; ++t) {
+          const int s = p.tap_src[t];
+          const uint32_t a_tap = a_base + static_cast<uint32_t>(s) * hp.a_src_bytes +
+                                 static_cast<uint32_t>((p.tap_dy[t] - hp.dy_min[s]) * hp.hal_w +
+                                                       (p.tap_dx[t] - hp.dx_min[s])) * 16u;
+          const uint64_t bdesc = make_smem_desc(b_base + static_cast<uint32_t>(t) * hp.b_tap_bytes, 16, sbo_b, swz_b);
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(a_tap + 2u * k * hp.kslice_bytes, hp.kslice_bytes, sbo_a, 0);
+            umma_bf16(d_tmem, adesc, bdesc + 2u * k, p.idesc, (t | k) != 0);
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[acc]);
+      }
+      __syncwarp();
+      if (++stage == kAStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+      if (++acc == hp.n_acc) {
+        acc = 0;
+        aphase ^= 1;
+      }
+    }
+  } else {
+    const int group = (warp - 2) >> 2;       // 0 or 1: tiles alternate between the two epilogue warpgroups
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int bw = row & 7, bh = row >> 3;
+    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+    int acc = 0, i = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+      if ((i & 1) == group) {
+        const int tw = tile % p.tiles_w;
+        const int r = tile / p.tiles_w;
+        const int th = r % p.tiles_h;
+        const int n = r / p.tiles_h;
+        const int w = (tw << 3) + bw, h = (th << 4) + bh;
+        const bool valid = (w < p.W) && (h < p.H);
+        const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+        const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
+                                            (w >> p.add_shift) * p.add_sw)
+                                         : 0;
+        wait_bounded(&tfull[acc], aphase);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+        for (int c = 0; c < p.n_tile; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          if (valid) epilogue_chunk(p, v, c, n, h, w, o_off, a_off, scale);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      if (++acc == hp.n_acc) {
+        acc = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Decides whether a launch can take the halo path and fills its geometry; returns false to fall back.
+static bool plan_halo(const dfgan_conv_desc* d, HaloK& hp, int& smem_bytes) {
+  if (d->Cin != 32 && d->Cin != 64) return false;
+  if (d->Cout % 16 || d->Cout > 128) return false;
+  if (d->W < 8 || d->H < 16 || static_cast<long long>(d->W) * d->H < 64 * 64) return false;
+  int dy_max[DFGAN_MAX_SRC], dx_max[DFGAN_MAX_SRC];
+  bool used[DFGAN_MAX_SRC] = {false, false, false, false};
+  for (int s = 0; s < DFGAN_MAX_SRC; ++s) hp.dy_min[s] = hp.dx_min[s] = dy_max[s] = dx_max[s] = 0;
+  for (int t = 0; t < d->n_taps; ++t) {
+    const int s = d->taps[t].src;
+    if (s < 0 || s >= d->n_src) return false;
+    if (!used[s]) {
+      used[s] = true;
+      hp.dy_min[s] = dy_max[s] = d->taps[t].dy;
+      hp.dx_min[s] = dx_max[s] = d->taps[t].dx;
+    } else {
+      hp.dy_min[s] = d->taps[t].dy < hp.dy_min[s] ? d->taps[t].dy : hp.dy_min[s];
+      dy_max[s] = d->taps[t].dy > dy_max[s] ? d->taps[t].dy : dy_max[s];
+      hp.dx_min[s] = d->taps[t].dx < hp.dx_min[s] ? d->taps[t].dx : hp.dx_min[s];
+      dx_max[s] = d->taps[t].dx > dx_max[s] ? d->taps[t].dx : dx_max[s];
+    }
+  }
+  int ext_h = 0, ext_w = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    if (!used[s]) return false;
+    ext_h = dy_max[s] - hp.dy_min[s] > ext_h ? dy_max[s] - hp.dy_min[s] : ext_h;
+    ext_w = dx_max[s] - hp.dx_min[s] > ext_w ? dx_max[s] - hp.dx_min[s] : ext_w;
+  }
+  if (ext_h > 2 || ext_w > 2) return false;
+  hp.n_src = d->n_src;
+  hp.hal_w = 8 + ext_w, hp.hal_h = 16 + ext_h;
+  hp.kslice_bytes = static_cast<uint32_t>(hp.hal_w * hp.hal_h * 16);
+  hp.a_src_bytes = (hp.kslice_bytes * (d->Cin / 8) + 127u) & ~127u;
+  hp.b_tap_bytes = static_cast<uint32_t>(d->Cout) * d->Cin * 2u;
+  hp.n_acc = d->Cout <= 128 ? 4 : 2;
+  const size_t need = static_cast<size_t>(d->n_taps) * hp.b_tap_bytes + 2u * hp.n_src * hp.a_src_bytes + 1024 + 256;
+  if (need > kSmemBudget) return false;
+  smem_bytes = static_cast<int>(need);
+  return true;
+}
+
 static void brick_geometry(int W, int H, int& lbw, int& lbh) {
   int bw = 1;
   while (bw < W && bw < 16) bw <<= 1;
@@ -498,11 +726,39 @@ static uint32_t pow2_cols(int c) {
   return v;
 }
 
-constexpr size_t kSmemBudget = 200 * 1024;
-
 }  // namespace dfgan
 
 using namespace dfgan;
+
+static void fill_epilogue(ConvK& k, const dfgan_conv_desc* d) {
+  k.out = static_cast<__nv_bfloat16*>(d->out);
+  k.out_sw = d->out_sw, k.out_sh = d->out_sh, k.out_sn = d->out_sn;
+  k.bias = d->bias, k.scale_dev = d->scale_dev, k.scale_imm = d->scale_imm;
+  k.lrelu_pre = d->lrelu_pre, k.slope = d->slope;
+  k.aux = static_cast<__nv_bfloat16*>(d->aux);
+  k.addend = static_cast<const __nv_bfloat16*>(d->addend);
+  k.add_sw = d->add_sw, k.add_sh = d->add_sh, k.add_sn = d->add_sn;
+  k.add_shift = d->add_shift, k.add_scale = d->add_scale;
+  k.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
+  k.out2 = static_cast<__nv_bfloat16*>(d->out2);
+  k.post_mode = d->post_mode;
+  k.tab_ga = d->tab_ga, k.tab_ba = d->tab_ba, k.tab_gb = d->tab_gb, k.tab_bb = d->tab_bb;
+  k.tab_stride = d->tab_stride;
+  k.out_nchw = d->out_nchw, k.co_valid = d->co_valid, k.tanh_out = d->tanh_out;
+}
+
+// executed work of a launch: real output pixels x Cout x (taps * Cin) MACs; bytes = every source view read once
+// + weights + the outputs written (the algorithmic minimum for this launch)
+static double launch_bytes(const dfgan_conv_desc* d) {
+  const double pix = static_cast<double>(d->N) * d->H * d->W;
+  double bytes = 2.0 * d->w_rows * d->Cin;
+  for (int s = 0; s < d->n_src; ++s)
+    bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
+  bytes += pix * d->Cout * 2.0 * ((d->out != nullptr) + (d->aux != nullptr) + (d->out2 != nullptr)) +
+           (d->addend ? pix * d->Cout * 2.0 / (1 << (2 * d->add_shift)) : 0.0) +
+           (d->mask_src ? pix * d->Cout * 2.0 : 0.0) + (d->out_nchw ? pix * d->co_valid * 4.0 : 0.0);
+  return bytes;
+}
 
 extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -515,6 +771,54 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     return DFGAN_E_ARG;
   if (d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1) return DFGAN_E_SHAPE;
   const int BK = (d->Cin % 64 == 0) ? 64 : 32;
+  {
+    HaloK hp{};
+    int smem_halo = 0;
+    static const bool halo_off = getenv("DFGAN_NO_HALO") != nullptr;
+    if (!halo_off && d->n_tile_hint == 0 && plan_halo(d, hp, smem_halo)) {
+      ConvK k{};
+      ConvMaps maps{};
+      k.lbw = 3, k.lbh = 4;
+      k.tiles_w = (d->W + 7) / 8, k.tiles_h = (d->H + 15) / 16, k.tiles_n = d->N;
+      k.n_tiles_n = 1, k.total_tiles = k.tiles_w * k.tiles_h * k.tiles_n;
+      k.n_tile = d->Cout;
+      k.N = d->N, k.H = d->H, k.W = d->W, k.Cout = d->Cout;
+      k.n_taps = d->n_taps, k.n_chunks = 1;
+      for (int t = 0; t < d->n_taps; ++t) {
+        k.tap_src[t] = d->taps[t].src, k.tap_dy[t] = d->taps[t].dy, k.tap_dx[t] = d->taps[t].dx;
+        k.tap_wrow[t] = d->taps[t].wrow;
+      }
+      k.idesc = make_idesc_bf16(128, k.n_tile, 0, 0);
+      fill_epilogue(k, d);
+      for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
+        const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
+        if (v.C != d->Cin) return DFGAN_E_SHAPE;
+        int rc = make_map_halo(&maps.a[s], v, hp.hal_w, hp.hal_h);
+        if (rc) return rc;
+      }
+      int rc = make_map_2d(&maps.b, d->wpack, d->w_rows, d->Cin, d->Cin, k.n_tile);
+      if (rc) return rc;
+      int grid = k.total_tiles;
+      const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
+      if (grid > cap) grid = cap;
+      const double pix = static_cast<double>(d->N) * d->H * d->W;
+      ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, launch_bytes(d), stream);
+      cudaError_t e;
+      if (d->Cin == 64) {
+        e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        conv_halo_kernel<64><<<grid, kHaloThreads, smem_halo, stream>>>(maps, k, hp);
+      } else {
+        e = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        conv_halo_kernel<32><<<grid, kHaloThreads, smem_halo, stream>>>(maps, k, hp);
+      }
+      count_launch();
+      DFGAN_CUDA_CHECK_LAUNCH();
+      return DFGAN_OK;
+    }
+  }
+
   ConvK k{};
   ConvMaps maps{};
   brick_geometry(d->W, d->H, k.lbw, k.lbh);
@@ -555,20 +859,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   if (stages < 2) return DFGAN_E_SHAPE;
   k.n_stages = stages;
   k.tmem_cols = pow2_cols(2 * n_tile);
-  k.out = static_cast<__nv_bfloat16*>(d->out);
-  k.out_sw = d->out_sw, k.out_sh = d->out_sh, k.out_sn = d->out_sn;
-  k.bias = d->bias, k.scale_dev = d->scale_dev, k.scale_imm = d->scale_imm;
-  k.lrelu_pre = d->lrelu_pre, k.slope = d->slope;
-  k.aux = static_cast<__nv_bfloat16*>(d->aux);
-  k.addend = static_cast<const __nv_bfloat16*>(d->addend);
-  k.add_sw = d->add_sw, k.add_sh = d->add_sh, k.add_sn = d->add_sn;
-  k.add_shift = d->add_shift, k.add_scale = d->add_scale;
-  k.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
-  k.out2 = static_cast<__nv_bfloat16*>(d->out2);
-  k.post_mode = d->post_mode;
-  k.tab_ga = d->tab_ga, k.tab_ba = d->tab_ba, k.tab_gb = d->tab_gb, k.tab_bb = d->tab_bb;
-  k.tab_stride = d->tab_stride;
-  k.out_nchw = d->out_nchw, k.co_valid = d->co_valid, k.tanh_out = d->tanh_out;
+  fill_epilogue(k, d);
 
   for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
     const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
@@ -583,16 +874,8 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   int grid = k.total_tiles;
   const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
   if (grid > cap) grid = cap;
-  // executed work of this launch: real output pixels x Cout x (taps * Cin) MACs; bytes = every source view read
-  // once + weights + the outputs written (the algorithmic minimum for this launch)
   const double pix = static_cast<double>(d->N) * d->H * d->W;
-  double bytes = 2.0 * d->w_rows * d->Cin;
-  for (int s = 0; s < d->n_src; ++s)
-    bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
-  bytes += pix * d->Cout * 2.0 * ((d->out != nullptr) + (d->aux != nullptr) + (d->out2 != nullptr)) +
-           (d->addend ? pix * d->Cout * 2.0 / (1 << (2 * d->add_shift)) : 0.0) +
-           (d->mask_src ? pix * d->Cout * 2.0 : 0.0) + (d->out_nchw ? pix * d->co_valid * 4.0 : 0.0);
-  ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream);
+  ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, launch_bytes(d), stream);
   cudaError_t e;
   if (BK == 64) {
     e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

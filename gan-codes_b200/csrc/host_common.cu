@@ -52,6 +52,21 @@ int make_map_nhwc(CUtensorMap* m, const dfgan_view4& v, int bc, int bw, int bh, 
   return r == CUDA_SUCCESS ? DFGAN_OK : DFGAN_E_DRIVER;
 }
 
+int make_map_halo(CUtensorMap* m, const dfgan_view4& v, int bw, int bh) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return DFGAN_E_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) || (v.sw & 7) || (v.sh & 7) || (v.sn & 7) || (v.C & 7))
+    return DFGAN_E_ARG;
+  cuuint64_t dims[5] = {8, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)(v.C / 8), (cuuint64_t)v.N};
+  cuuint64_t strides[4] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, 16, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[5] = {8, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)(v.C / 8), 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(v.ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DFGAN_OK : DFGAN_E_DRIVER;
+}
+
 int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int bc, int brows) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return DFGAN_E_DRIVER;

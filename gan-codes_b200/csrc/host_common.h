@@ -34,6 +34,9 @@ int num_sms();
 
 // bf16 NHWC view -> 4-D tiled tensor map with box {bc, bw, bh, bn}; OOB elements read as zero.
 int make_map_nhwc(CUtensorMap* m, const dfgan_view4& v, int bc, int bw, int bh, int bn);
+// bf16 NHWC view -> 5-D map {8 ch, W, H, C/8, N} with box {8, bw, bh, C/8, 1}, no swizzle: one load delivers
+// a halo tile as [channel slice][h][w][8 ch], the canonical no-swizzle K-major UMMA operand layout.
+int make_map_halo(CUtensorMap* m, const dfgan_view4& v, int bw, int bh);
 // bf16 row-major matrix [rows][cols] -> 2-D tiled tensor map with box {bc, brows}.
 int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int bc, int brows);
 

@@ -58,7 +58,7 @@ for nm in ("affine2_fwd", "affine2_bwd", "pool", "dres_bwd", "dot", "im2col3", "
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 torch.manual_seed(0)
 G, D = Generator(32, 100).cuda(), Discriminator(32).cuda()
-tr = DFGANTrainer(G, D, B)
+tr = DFGANTrainer(G, D, B, use_graph=False)
 img = (torch.randn(B, 3, 256, 256, device="cuda") * 0.5).clamp(-1, 1)
 sent, noise = torch.randn(B, 256, device="cuda") * 0.3, torch.randn(B, 100, device="cuda")
 for _ in range(3):

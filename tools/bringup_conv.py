@@ -161,7 +161,7 @@ def subpixel():
     import torch.nn.functional as F
     from gan_codes_b200 import convops as co, kernels as K
     ok = True
-    for (N, C, Kc, H) in [(2, 64, 32, 16), (3, 256, 128, 8), (2, 128, 64, 32)]:
+    for (N, C, Kc, H) in [(2, 64, 32, 16), (3, 256, 128, 8), (2, 128, 64, 32), (2, 64, 32, 64)]:
         x = torch.randn(N, C, H, H, device="cuda").bfloat16()
         w = (torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5))
         b = torch.randn(Kc, device="cuda")
@@ -365,6 +365,62 @@ def optim():
         e = _rel(p - pr.detach(), torch.zeros_like(p)) if False else ((p - pr.detach()).abs().max() / 4e-4).item()
         print(f"adam it{it}: max |dp| / lr = {e:.3e}, sumsq rel {abs(ss.item() - (gi ** 2).sum().item()) / (gi ** 2).sum().item():.2e}")
         ok &= e < 1e-2
+    return ok
+
+
+@case
+def halo():
+    """High-resolution narrow layers take the halo kernel (conv_halo_kernel); every tap-list flavour is checked
+    against torch and against the generic kernel (forced with an explicit n_tile)."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co
+    ok = True
+    for (N, C, Kc, H) in [(2, 32, 32, 64), (2, 64, 64, 64), (1, 64, 16, 128), (2, 32, 64, 96), (1, 64, 128, 64)]:
+        x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        w = (torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5)).bfloat16()
+        b = torch.randn(Kc, device="cuda")
+        ref = F.conv2d(x.float(), w.float(), b, padding=1)
+        o1 = torch.empty(N, H, H, Kc, device="cuda", dtype=torch.bfloat16)
+        o2 = torch.empty_like(o1)
+        xn, wp = _nhwc(x), _pack(w)
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o1, bias=b)
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o2, bias=b, n_tile=Kc)
+        w1 = (torch.randn(Kc, C, 1, 1, device="cuda") / C ** 0.5).bfloat16()
+        o3 = torch.empty_like(o1)
+        co.conv_run([xn], co.taps_1x1(), _pack(w1), Kc, o3)
+        torch.cuda.synchronize()
+        e = (_rel(o1.permute(0, 3, 1, 2), ref), _rel(o1, o2), _rel(o3.permute(0, 3, 1, 2), F.conv2d(x.float(), w1.float())))
+        print(f"halo 3x3 N{N} C{C} K{Kc} {H}: vs torch {e[0]:.3e} vs generic {e[1]:.3e} 1x1 {e[2]:.3e}")
+        ok &= e[0] < 8e-3 and e[1] < 1e-3 and e[2] < 8e-3
+    # 4x4 stride 2 over four parity views, its phase data gradient, the pooled 1x1 shortcut
+    for (N, C, Kc, H) in [(2, 32, 64, 256), (1, 64, 64, 128)]:
+        x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        w4 = (torch.randn(Kc, C, 4, 4, device="cuda") / (4 * C ** 0.5)).bfloat16()
+        ref = F.leaky_relu(F.conv2d(x.float(), w4.float(), None, stride=2, padding=1), 0.2)
+        out = torch.empty(N, H // 2, H // 2, Kc, device="cuda", dtype=torch.bfloat16)
+        pv = co.parity_views(_nhwc(x))
+        co.conv_run(pv, co.taps_4x4s2(Kc), _pack(w4), Kc, out, lrelu_pre=True)
+        ws = (torch.randn(Kc, C, 1, 1, device="cuda") / C ** 0.5).bfloat16()
+        bs = torch.randn(Kc, device="cuda")
+        sref = F.avg_pool2d(F.conv2d(x.float(), ws.float(), bs), 2)
+        so = torch.empty_like(out)
+        co.conv_run(pv, [(i, 0, 0, 0) for i in range(4)], _pack(ws, scale=0.25), Kc, so, bias=bs)
+        e = [_rel(out.permute(0, 3, 1, 2), ref), _rel(so.permute(0, 3, 1, 2), sref)]
+        if Kc <= 64:
+            g2 = torch.randn(N, Kc, H // 2, H // 2, device="cuda").bfloat16()
+            gref = F.conv_transpose2d(g2.float(), w4.float(), stride=2, padding=1)
+            gx = torch.zeros(N, H, H, C, device="cuda", dtype=torch.bfloat16)
+            wd, g2n = _pack(w4, True), _nhwc(g2)
+            add = torch.randn(N, H // 2, H // 2, C, device="cuda").bfloat16()
+            for a in (0, 1):
+                for c in (0, 1):
+                    co.conv_run([g2n], co.taps_4x4s2_dgrad(C, a, c), wd, C, gx[:, a::2, c::2, :], addend=add, add_scale=0.25)
+            gref = gref + 0.25 * F.interpolate(add.float().permute(0, 3, 1, 2), scale_factor=2)
+            e.append(_rel(gx.permute(0, 3, 1, 2), gref))
+        torch.cuda.synchronize()
+        print(f"halo 4s2 N{N} C{C} K{Kc} {H}: " + " ".join(f"{v:.3e}" for v in e))
+        ok &= max(e) < 8e-3
     return ok
 
 
