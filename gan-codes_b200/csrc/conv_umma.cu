@@ -201,28 +201,31 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int k_iters = p.n_taps * p.n_chunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState ps;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
-        const int tw = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int tn = mt / p.tiles_h;
-        const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn * (128 >> (p.lbw + p.lbh));
-        for (int t = 0; t < p.n_taps; ++t) {
-          const CUtensorMap* ma = &maps.a[p.tap_src[t]];
-          const int wy = h0 + p.tap_dy[t], wx = w0 + p.tap_dx[t];
-          const int brow = p.tap_wrow[t] + nt * p.n_tile;
-          for (int c = 0; c < p.n_chunks; ++c) {
-            wait_bounded(&empty[ps.stage], ps.phase ^ 1);
-            uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
+    // whole warp runs the loop (coordinates stay warp-uniform -> uniform registers), one elected lane issues
+    const bool leader = elect_one();
+    PipeState ps;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tn = mt / p.tiles_h;
+      const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn * (128 >> (p.lbw + p.lbh));
+      for (int t = 0; t < p.n_taps; ++t) {
+        const CUtensorMap* ma = &maps.a[p.tap_src[t]];
+        const int wy = h0 + p.tap_dy[t], wx = w0 + p.tap_dx[t];
+        const int brow = p.tap_wrow[t] + nt * p.n_tile;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          wait_bounded(&empty[ps.stage], ps.phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
+          if (leader) {
             mbar_expect_tx(&full[ps.stage], stage_bytes);
             tma_load_4d(sa, ma, &full[ps.stage], c * BK, wx, wy, n0);
             tma_load_2d(sa + p.a_bytes, &maps.b, &full[ps.stage], c * BK, brow);
-            ps.advance(p.n_stages);
           }
+          __syncwarp();
+          ps.advance(p.n_stages);
         }
       }
     }
@@ -236,22 +239,24 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       wait_bounded(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      // descriptors are computed warp-uniformly (uniform registers); only the tcgen05 instructions are
+      // predicated on the elected lane -- see the note in conv_halo_kernel
+      const bool leader = elect_one();
       for (int it = 0; it < k_iters; ++it) {
         wait_bounded(&full[ps.stage], ps.phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
-          const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, swz);
-          const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, sbo, swz);
+        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
+        const uint64_t adesc = make_smem_desc(a_addr, 16, sbo, swz);
+        const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, sbo, swz);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0);
-          umma_commit(&empty[ps.stage]);
+        for (int k = 0; k < BK / 16; ++k) {
+          if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0);
         }
+        if (leader) umma_commit(&empty[ps.stage]);
         __syncwarp();
         ps.advance(p.n_stages);
       }
-      if (lane == 0) umma_commit(&tfull[as]);
+      if (leader) umma_commit(&tfull[as]);
       __syncwarp();
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -375,7 +380,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   const int blocks_per_tile = 128 >> p.lcb;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       PipeState ps;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int ks = item % p.k_splits;
@@ -394,18 +400,22 @@ __global__ void __launch_bounds__(kConvThreads, 1)
           const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn * (128 >> (p.lbw + p.lbh));
           wait_bounded(&empty[ps.stage], ps.phase ^ 1);
           uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
-          mbar_expect_tx(&full[ps.stage], stage_bytes);
+          if (leader) mbar_expect_tx(&full[ps.stage], stage_bytes);
           for (int b = 0; b < blocks_per_tile; ++b) {
             int rb = mt * blocks_per_tile + b;
             if (rb >= p.row_blocks) rb = mt * blocks_per_tile;  // padding block: reload a valid one
             const int t = rb / p.blocks_per_tap;
             const int c0 = (rb % p.blocks_per_tap) << p.lcb;
-            tma_load_4d(sa + b * p.a_blk_bytes, &maps.a[p.tap_src[t]], &full[ps.stage], c0,
-                        w0 + p.tap_dx[t], h0 + p.tap_dy[t], n0);
+            if (leader)
+              tma_load_4d(sa + b * p.a_blk_bytes, &maps.a[p.tap_src[t]], &full[ps.stage], c0,
+                          w0 + p.tap_dx[t], h0 + p.tap_dy[t], n0);
           }
-          for (int b = 0; b < p.n_blocks_b; ++b)
-            tma_load_4d(sa + p.a_bytes + b * p.b_blk_bytes, &maps.g, &full[ps.stage],
-                        nt * p.n_tile + b * p.cbg, w0, h0, n0);
+          for (int b = 0; b < p.n_blocks_b; ++b) {
+            if (leader)
+              tma_load_4d(sa + p.a_bytes + b * p.b_blk_bytes, &maps.g, &full[ps.stage],
+                          nt * p.n_tile + b * p.cbg, w0, h0, n0);
+          }
+          __syncwarp();
           ps.advance(p.n_stages);
         }
       }
@@ -425,24 +435,25 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       wait_bounded(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
+      const bool leader = elect_one();   // descriptors stay warp-uniform, see conv_halo_kernel
       for (int pt = pt0; pt < pt1; ++pt) {
         wait_bounded(&full[ps.stage], ps.phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
-          const uint64_t adesc = make_smem_desc(a_addr, p.a_blk_bytes, sbo_a, swz_a);
-          const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.b_blk_bytes, sbo_b, swz_b);
+        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
+        const uint64_t adesc = make_smem_desc(a_addr, p.a_blk_bytes, sbo_a, swz_a);
+        const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, p.b_blk_bytes, sbo_b, swz_b);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)  // 16 pixels per MMA = two 8-pixel swizzle atoms
+        for (int k = 0; k < 8; ++k) {  // 16 pixels per MMA = two 8-pixel swizzle atoms
+          if (leader)
             umma_bf16(d_tmem, adesc + static_cast<uint64_t>((2u * sbo_a * k) >> 4),
                       bdesc + static_cast<uint64_t>((2u * sbo_b * k) >> 4), p.idesc,
                       (pt > pt0) || (k != 0));
-          umma_commit(&empty[ps.stage]);
         }
+        if (leader) umma_commit(&empty[ps.stage]);
         __syncwarp();
         ps.advance(p.n_stages);
       }
-      if (lane == 0) umma_commit(&tfull[as]);
+      if (leader) umma_commit(&tfull[as]);
       __syncwarp();
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -492,25 +503,36 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 constexpr size_t kSmemBudget = 200 * 1024;
 
 // ---------------------------------------------------------------------------------------------
-// Halo variant for the high-resolution, narrow layers (C_in <= 64, where the tap-list kernel above is bound
-// by re-reading the A tile from L2 once per filter tap).  An M tile is a 16(h) x 8(w) pixel brick; for every
-// source view ONE 5-D TMA load brings the brick plus its halo into shared memory as
-// [channel slice of 8][h][w][8 ch] -- the canonical no-swizzle K-major layout, in which a filter tap (dy,dx)
-// is just a different start address (SBO = one halo row, LBO = one channel slice).  All taps of the packed
-// weight matrix stay resident in shared memory for the life of the CTA.  Per 128 output pixels the kernel
-// moves (16+2)(8+2) * C_in * 2 bytes instead of taps * 128 * (C_in + n_tile) * 2.
+// Halo variant for the high-resolution, narrow layers (C_in <= 64), where the tap-list kernel above is bound
+// by the TMA engine: it delivers about one box row (<= 128 B) per ~4.5 cycles per SM whatever the row size
+// (measured: 1152 rows per 128-pixel tile for a 3x3 layer).  Here an M tile is a 16(h) x 8(w) pixel brick and
+// the brick PLUS ITS HALO is loaded once per source view as pixel rows of C_in*2 bytes in the swizzled
+// K-major layout; a filter tap (dy,dx) is then only a different start row of the UMMA descriptor:
+//   mode 0: one halo tile per dx (row pitch 8 pixels): every tap start is swizzle-atom aligned      (432 rows)
+//   mode 1: one halo tile, row pitch 16 pixels: dy shifts are atom aligned, dx shifts use the          (288 rows)
+//           descriptor's base-offset field
+//   mode 2: one halo tile, row pitch 8 + halo: arbitrary row shifts, base-offset field per tap         (180 rows)
+// All taps of the packed weight matrix stay resident in shared memory for the life of the CTA.
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 two epilogue warpgroups alternating tiles over
-// up to four TMEM accumulator stages (the epilogue, not the MMA, bounds these layers).
+// up to four TMEM accumulator stages.
 constexpr int kHaloThreads = 320;
 
 struct HaloK {
   int dy_min[DFGAN_MAX_SRC], dx_min[DFGAN_MAX_SRC];
-  int n_src, hal_w, hal_h;
-  uint32_t a_src_bytes;   // one source's halo tile, padded to 128 B
-  uint32_t kslice_bytes;  // hal_h * hal_w * 16
-  uint32_t b_tap_bytes;   // n_tile * C_in * 2
-  int n_acc;              // TMEM accumulator stages (2 or 4)
+  int n_parts[DFGAN_MAX_SRC];  // halo tiles per source (mode 0: one per dx)
+  int part_base[DFGAN_MAX_SRC];
+  int n_src, n_parts_total, mode;
+  int pitch, hal_h;            // pixels per halo row in shared memory, halo rows
+  uint32_t a_part_bytes;       // hal_h * pitch * C_in * 2, padded to 1024 B
+  uint32_t b_tap_bytes;        // n_tile * C_in * 2
+  int n_acc;                   // TMEM accumulator stages (2 or 4)
+  int n_a_stages;              // halo tiles in flight (TMA latency ~2 us: 2 is not enough)
+  int use_bo;
 };
+
+__device__ __forceinline__ uint64_t with_base_offset(uint64_t desc, uint32_t saddr) {
+  return desc | (static_cast<uint64_t>((saddr >> 7) & 7u) << 49);
+}
 
 template <int CIN>
 __global__ void __launch_bounds__(kHaloThreads, 1)
@@ -519,18 +541,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  constexpr int kAStages = 2;
+  const int kAStages = hp.n_a_stages;
+  constexpr uint32_t kRowBytes = CIN * 2u;
   const uint32_t b_bytes = static_cast<uint32_t>(p.n_taps) * hp.b_tap_bytes;
-  const uint32_t a_stage_bytes = static_cast<uint32_t>(hp.n_src) * hp.a_src_bytes;
+  const uint32_t a_stage_bytes = static_cast<uint32_t>(hp.n_parts_total) * hp.a_part_bytes;
   uint8_t* sB = smem;
   uint8_t* sA = smem + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kAStages * a_stage_bytes);
-  uint64_t* full = bars;               // [2]
-  uint64_t* empty = bars + 2;          // [2]
-  uint64_t* tfull = bars + 4;          // [4]
-  uint64_t* tempty = bars + 8;         // [4]
-  uint64_t* bfull = bars + 12;         // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* full = bars;               // [8]
+  uint64_t* empty = bars + 8;          // [8]
+  uint64_t* tfull = bars + 16;         // [4]
+  uint64_t* tempty = bars + 20;        // [4]
+  uint64_t* bfull = bars + 24;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -561,57 +584,69 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bfull, b_bytes);
-      for (int t = 0; t < p.n_taps; ++t)
-        tma_load_2d(sB + static_cast<size_t>(t) * hp.b_tap_bytes, &maps.b, bfull, 0, p.tap_wrow[t]);
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = static_cast<uint32_t>(hp.n_src) * hp.kslice_bytes * (CIN / 8);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tw = tile % p.tiles_w;
-        const int r = tile / p.tiles_w;
-        const int th = r % p.tiles_h;
-        const int n = r / p.tiles_h;
-        wait_bounded(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], tx);
-        uint8_t* dst = sA + static_cast<size_t>(stage) * a_stage_bytes;
-        for (int s = 0; s < hp.n_src; ++s)
-          tma_load_5d(dst + static_cast<size_t>(s) * hp.a_src_bytes, &maps.a[s], &full[stage], 0,
-                      (tw << 3) + hp.dx_min[s], (th << 4) + hp.dy_min[s], 0, n);
-        if (++stage == kAStages) {
-          stage = 0;
-          phase ^= 1;
+    const bool leader = elect_one();
+    if (leader) mbar_expect_tx(bfull, b_bytes);
+    for (int t = 0; t < p.n_taps; ++t) {
+      if (leader) tma_load_2d(sB + static_cast<size_t>(t) * hp.b_tap_bytes, &maps.b, bfull, 0, p.tap_wrow[t]);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = static_cast<uint32_t>(hp.n_parts_total) * hp.hal_h * hp.pitch * kRowBytes;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int tw = tile % p.tiles_w;
+      const int r = tile / p.tiles_w;
+      const int th = r % p.tiles_h;
+      const int n = r / p.tiles_h;
+      wait_bounded(&empty[stage], phase ^ 1);
+      if (leader) mbar_expect_tx(&full[stage], tx);
+      uint8_t* dst = sA + static_cast<size_t>(stage) * a_stage_bytes;
+      for (int s = 0; s < hp.n_src; ++s)
+        for (int q = 0; q < hp.n_parts[s]; ++q) {
+          if (leader)
+            tma_load_4d(dst + static_cast<size_t>(hp.part_base[s] + q) * hp.a_part_bytes, &maps.a[s], &full[stage],
+                        0, (tw << 3) + hp.dx_min[s] + q, (th << 4) + hp.dy_min[s], n);
         }
+      __syncwarp();
+      if (++stage == kAStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t swz_b = (CIN == 64) ? SWZ_128B : SWZ_64B;
-    constexpr uint32_t sbo_b = 8u * CIN * 2u;
-    const uint32_t sbo_a = static_cast<uint32_t>(hp.hal_w) * 16u;
+    constexpr uint32_t swz = (CIN == 64) ? SWZ_128B : SWZ_64B;
+    constexpr uint32_t sbo_b = 8u * kRowBytes;
+    const uint32_t sbo_a = static_cast<uint32_t>(hp.pitch) * kRowBytes;
+    // Everything the MMA needs (descriptors, TMEM address) is computed by the WHOLE warp so that it is
+    // warp-uniform and lives in uniform registers; only the tcgen05 instructions themselves sit under the
+    // elected-lane predicate.  (Computing descriptors inside `if (lane == 0)` makes the compiler wrap every
+    // UTCHMMA in an ELECT/R2UR waterfall loop -- ~150 cycles per MMA, the former bound of this kernel.)
     int stage = 0, acc = 0;
     uint32_t phase = 0, aphase = 0;
     wait_bounded(bfull, 0);
+    const uint32_t b_base = smem_u32(sB);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       wait_bounded(&tempty[acc], aphase ^ 1);
       wait_bounded(&full[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-        const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * a_stage_bytes);
-        const uint32_t b_base = smem_u32(sB);
-        for (int t = 0; t < p.n_taps; ++t) {
-          const int s = p.tap_src[t];
-          const uint32_t a_tap = a_base + static_cast<uint32_t>(s) * hp.a_src_bytes +
-                                 static_cast<uint32_t>((p.tap_dy[t] - hp.dy_min[s]) * hp.hal_w +
-                                                       (p.tap_dx[t] - hp.dx_min[s])) * 16u;
-          const uint64_t bdesc = make_smem_desc(b_base + static_cast<uint32_t>(t) * hp.b_tap_bytes, 16, sbo_b, swz_b);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+      const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * a_stage_bytes);
+      const bool leader = elect_one();
+      for (int t = 0; t < p.n_taps; ++t) {
+        const int s = p.tap_src[t];
+        const int ddx = p.tap_dx[t] - hp.dx_min[s], ddy = p.tap_dy[t] - hp.dy_min[s];
+        const int part = hp.part_base[s] + (hp.mode == 0 ? ddx : 0);
+        const int row0 = ddy * hp.pitch + (hp.mode == 0 ? 0 : ddx);
+        const uint32_t a_tap = a_base + static_cast<uint32_t>(part) * hp.a_part_bytes +
+                               static_cast<uint32_t>(row0) * kRowBytes;
+        uint64_t adesc = make_smem_desc(a_tap, 16, sbo_a, swz);
+        if (hp.use_bo) adesc = with_base_offset(adesc, a_tap);
+        const uint64_t bdesc = make_smem_desc(b_base + static_cast<uint32_t>(t) * hp.b_tap_bytes, 16, sbo_b, swz);
 #pragma unroll
-          for (int k = 0; k < CIN / 16; ++k) {
-            const uint64_t adesc = make_smem_desc(a_tap + 2u * k * hp.kslice_bytes, hp.kslice_bytes, sbo_a, 0);
-            umma_bf16(d_tmem, adesc, bdesc + 2u * k, p.idesc, (t | k) != 0);
-          }
+        for (int k = 0; k < CIN / 16; ++k) {
+          if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
         }
+      }
+      if (leader) {
         umma_commit(&empty[stage]);
         umma_commit(&tfull[acc]);
       }
@@ -675,6 +710,10 @@ static bool plan_halo(const dfgan_conv_desc* d, HaloK& hp, int& smem_bytes) {
   if (d->Cin != 32 && d->Cin != 64) return false;
   if (d->Cout % 16 || d->Cout > 128) return false;
   if (d->W < 8 || d->H < 16 || static_cast<long long>(d->W) * d->H < 64 * 64) return false;
+  // mode 2 is the default: tcgen05 applies the swizzle XOR to absolute shared-memory address bits, so a
+  // descriptor may start at any 16-byte-aligned row of a TMA-written swizzled tile (verified on B200 by
+  // tools/bringup_conv.py halo for all three modes)
+  static const int mode_env = getenv("DFGAN_HALO_MODE") ? atoi(getenv("DFGAN_HALO_MODE")) : 2;
   int dy_max[DFGAN_MAX_SRC], dx_max[DFGAN_MAX_SRC];
   bool used[DFGAN_MAX_SRC] = {false, false, false, false};
   for (int s = 0; s < DFGAN_MAX_SRC; ++s) hp.dy_min[s] = hp.dx_min[s] = dy_max[s] = dx_max[s] = 0;
@@ -699,15 +738,28 @@ static bool plan_halo(const dfgan_conv_desc* d, HaloK& hp, int& smem_bytes) {
     ext_w = dx_max[s] - hp.dx_min[s] > ext_w ? dx_max[s] - hp.dx_min[s] : ext_w;
   }
   if (ext_h > 2 || ext_w > 2) return false;
+  hp.mode = ext_w == 0 ? 0 : mode_env;   // no dx shift: a single aligned tile is all three modes at once
   hp.n_src = d->n_src;
-  hp.hal_w = 8 + ext_w, hp.hal_h = 16 + ext_h;
-  hp.kslice_bytes = static_cast<uint32_t>(hp.hal_w * hp.hal_h * 16);
-  hp.a_src_bytes = (hp.kslice_bytes * (d->Cin / 8) + 127u) & ~127u;
+  hp.hal_h = 16 + ext_h;
+  hp.pitch = hp.mode == 0 ? 8 : (hp.mode == 1 ? 16 : 8 + ext_w);
+  int total = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    hp.part_base[s] = total;
+    hp.n_parts[s] = hp.mode == 0 ? (dx_max[s] - hp.dx_min[s] + 1) : 1;
+    total += hp.n_parts[s];
+  }
+  hp.n_parts_total = total;
+  hp.a_part_bytes = (static_cast<uint32_t>(hp.hal_h * hp.pitch * d->Cin * 2) + 1023u) & ~1023u;
   hp.b_tap_bytes = static_cast<uint32_t>(d->Cout) * d->Cin * 2u;
-  hp.n_acc = d->Cout <= 128 ? 4 : 2;
-  const size_t need = static_cast<size_t>(d->n_taps) * hp.b_tap_bytes + 2u * hp.n_src * hp.a_src_bytes + 1024 + 256;
-  if (need > kSmemBudget) return false;
-  smem_bytes = static_cast<int>(need);
+  hp.n_acc = 4;
+  hp.use_bo = getenv("DFGAN_HALO_BO") != nullptr && hp.mode != 0;
+  const size_t fixed = static_cast<size_t>(d->n_taps) * hp.b_tap_bytes + 1024 + 512;
+  const size_t per_stage = static_cast<size_t>(total) * hp.a_part_bytes;
+  const size_t cap = 220 * 1024;
+  if (fixed + 2 * per_stage > cap) return false;
+  int stages = static_cast<int>((cap - fixed) / per_stage);
+  hp.n_a_stages = stages > 8 ? 8 : stages;
+  smem_bytes = static_cast<int>(fixed + hp.n_a_stages * per_stage);
   return true;
 }
 
@@ -793,7 +845,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
         const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
         if (v.C != d->Cin) return DFGAN_E_SHAPE;
-        int rc = make_map_halo(&maps.a[s], v, hp.hal_w, hp.hal_h);
+        int rc = make_map_nhwc(&maps.a[s], v, d->Cin, hp.pitch, hp.hal_h, 1);
         if (rc) return rc;
       }
       int rc = make_map_2d(&maps.b, d->wpack, d->w_rows, d->Cin, d->Cin, k.n_tile);
@@ -830,8 +882,10 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     const long long m_tiles = static_cast<long long>((d->W + BW - 1) / BW) * ((d->H + BH - 1) / BH) *
                               ((d->N + BN - 1) / BN);
     n_tile = d->Cout <= 256 ? d->Cout : 256;
+    // (halving N doubles the A-tile traffic and halves the tensor-pipe efficiency of each MMA, so only do it
+    // while fewer than half of the SMs would have work)
     while (n_tile > 64 && n_tile % 32 == 0 && d->Cout % (n_tile / 2) == 0 &&
-           m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
+           2 * m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
       n_tile /= 2;
   }
   if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return DFGAN_E_SHAPE;
