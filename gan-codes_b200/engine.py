@@ -59,15 +59,23 @@ class FlatState:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
-    def optimizer_step(self, world: int = 1) -> None:
-        """(all-reduce) -> global L2 norm -> clip -> Adam, all on the flat buffers."""
+    def reduce(self, world: int) -> None:
+        """Data-parallel exchange: ONE all-reduce (sum) of the flat gradient; the 1/world factor is applied
+        inside the Adam kernel.  Issued eagerly, never inside a CUDA graph."""
         if world > 1:
             torch.distributed.all_reduce(self.grad)
+
+    def apply(self, world: int = 1) -> None:
+        """global L2 norm -> clip -> Adam on the flat buffers (two kernels)."""
         self.sumsq.zero_()
         K.sqnorm(self.grad, self.sumsq)
         self.step_count.add_(1)
         K.adam_step(self.flat, self.grad, self.m, self.v, self.sumsq, self.step_count, lr=self.lr,
                     gscale=1.0 / world, max_norm=self.clip, b1=self.betas[0], b2=self.betas[1], eps=self.eps)
+
+    def optimizer_step(self, world: int = 1) -> None:
+        self.reduce(world)
+        self.apply(world)
 
 
 class DFGANTrainer:
@@ -121,9 +129,15 @@ class DFGANTrainer:
         g_emb = torch.cat((ge[:b], ge[2 * b - 1:]), dim=0)
         g_emb[:b - 1] += ge[b:2 * b - 1]
         dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_emb), self.ds.grads, False)
-        self.ds.optimizer_step(self.world)
-        dpk.refresh(dp)
         return loss
+
+    def _d_update(self):
+        self.ds.apply(self.world)
+        self.dpk.refresh(self.ds.params)
+
+    def _g_update(self):
+        self.gs.apply(self.world)
+        self.gpk.refresh(self.gs.params)
 
     def _gp_step(self, images, sent):
         b = self.batch
@@ -143,8 +157,6 @@ class DFGANTrainer:
         self.ds.zero_grad()
         t_emb = dnet.trunk_tangent(dpk, dp, tctx, cots, gx, coef, self.ds.grads)
         dnet.head_tangent(dpk, dp, hctx, cots, dnet.embeds_to_nchw(t_emb), g_sent, coef, self.ds.grads)
-        self.ds.optimizer_step(self.world)
-        dpk.refresh(dp)
         return loss
 
     def _g_step(self, sent):
@@ -159,17 +171,60 @@ class DFGANTrainer:
         g_img = dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_embed), None, True)
         self.gs.zero_grad()
         gnet.generator_backward(self.gpk, self.gs.params, self.mlp, self.g_ctx, g_img, self.gs.grads)
-        self.gs.optimizer_step(self.world)
-        self.gpk.refresh(self.gs.params)
         self.g_ctx = {}
         return loss
 
     # ------------------------------------------------------------------------------------ public
-    def _body(self, images, sent, noise) -> Dict[str, torch.Tensor]:
-        d_loss = self._d_step(images, sent, noise)
-        gp_loss = self._gp_step(images, sent)
-        g_loss = self._g_step(sent)
-        return {"d_loss": d_loss, "gp_loss": gp_loss, "g_loss": g_loss}
+    # The iteration as four segments separated by the three data-parallel gradient exchanges.  With one GPU the
+    # segments are captured as ONE CUDA graph; with several each segment is its own graph and the NCCL
+    # all-reduces run eagerly between the replays (NCCL is never captured).
+    def _segments(self, images, sent, noise):
+        out = self._seg_out
+
+        def s0():
+            out["d_loss"] = self._d_step(images, sent, noise)
+
+        def s1():
+            self._d_update()
+            out["gp_loss"] = self._gp_step(images, sent)
+
+        def s2():
+            self._d_update()
+            out["g_loss"] = self._g_step(sent)
+
+        def s3():
+            self._g_update()
+        return [(s0, self.ds), (s1, self.ds), (s2, self.gs), (s3, None)]
+
+    def _run_eager(self, images, sent, noise) -> Dict[str, torch.Tensor]:
+        self._seg_out = {}
+        for fn, st in self._segments(images, sent, noise):
+            fn()
+            if st is not None:
+                st.reduce(self.world)
+        return self._seg_out
+
+    def _capture(self) -> None:
+        self._seg_out = {}
+        segs = self._segments(*self._in)
+        torch.cuda.synchronize()
+        if self.world == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for fn, _ in segs:
+                    fn()
+            self._graphs = [(g, None)]
+        else:
+            self._graphs = []
+            pool = None
+            for fn, st in segs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    fn()
+                pool = g.pool()
+                self._graphs.append((g, st))
+        self._graph = self._graphs[0][0]
+        self._graph_out = self._seg_out
 
     @torch.no_grad()
     def step(self, images: torch.Tensor, sentence_embeds: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -188,15 +243,14 @@ class DFGANTrainer:
             dst.copy_(src, non_blocking=True)
         if not self.use_graph or self._eager_calls < 2:
             self._eager_calls += 1
-            self.last = self._body(*self._in)
+            self.last = self._run_eager(*self._in)
             return self.last
         if self._graph is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._graph_out = self._body(*self._in)
-            self._graph = g
-        self._graph.replay()
+            self._capture()
+        for g, st in self._graphs:
+            g.replay()
+            if st is not None:
+                st.reduce(self.world)
         self.last = self._graph_out
         return self.last
 
@@ -204,7 +258,10 @@ class DFGANTrainer:
     def gp_step(self, images: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
         """MA-GP discriminator update only (BASELINE config 4)."""
         dev = self.gs.flat.device
-        return self._gp_step(images.to(dev, F32).contiguous(), sentence_embeds.to(dev, F32).contiguous())
+        loss = self._gp_step(images.to(dev, F32).contiguous(), sentence_embeds.to(dev, F32).contiguous())
+        self.ds.reduce(self.world)
+        self._d_update()
+        return loss
 
     @torch.no_grad()
     def sample(self, noise: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
