@@ -985,7 +985,10 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   const int base_items = k.n_tiles_m * k.n_tiles_n;
   int ks = d->k_splits;
   if (ks <= 0) {
-    ks = (2 * num_sms() + base_items - 1) / base_items;
+    // exactly one wave of work items: every split ends in 128 x n_tile fp32 atomics, and the measured optimum
+    // (tools/prof_wgrad.py) is items ~= #SMs for the wide layers; narrow layers (few row tiles) keep more
+    // splits because their main loop, not the atomics, dominates
+    ks = base_items >= 8 ? num_sms() / base_items : (2 * num_sms() + base_items - 1) / base_items;
     // keep at least 4 pixel tiles per split so the accumulate chain amortises the epilogue
     int max_ks = k.pix_tiles / 4;
     if (max_ks < 1) max_ks = 1;

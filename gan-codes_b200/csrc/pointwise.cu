@@ -37,19 +37,78 @@ __device__ __forceinline__ bf8 ldf8(const float* p) {
 }
 __device__ __forceinline__ float dlrelu(float pre, float slope) { return pre > 0.f ? 1.f : slope; }
 
-// Sum `acc` over all threads of the block that share (threadIdx.x % tpp) and atomically add the result to
-// dst[8] (thread with pixel-lane 0 does the add).  red: shared float[kPwThreads * 8].
-__device__ __forceinline__ void block_reduce8(const bf8& acc, float* red, int tpp, float* dst, float scale) {
-  const int tid = threadIdx.x;
-  __syncthreads();
+// 4-channel (8-byte) variants for the register-heavy backward kernel: half the per-thread state of the 8-wide
+// form, which is what lets four 256-thread blocks share an SM (a streaming kernel needs the occupancy).
+struct bf4 {
+  float v[4];
+};
+__device__ __forceinline__ bf4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  bf4 r;
+  unpack_bf16x2(u.x, r.v[0], r.v[1]);
+  unpack_bf16x2(u.y, r.v[2], r.v[3]);
+  return r;
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const bf4& r) {
+  uint2 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]);
+  u.y = pack_bf16x2(r.v[2], r.v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ bf4 ldf4(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  return bf4{{a.x, a.y, a.z, a.w}};
+}
+// block_reduce8 for 4-wide accumulators (tpp = C / 4 threads per pixel); red: shared float[kPwThreads * 4]
+__device__ __forceinline__ void block_reduce4(bf4 acc, float* red, int tpp, float* dst) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_warp = tpp < 32 ? tpp : 32;
+  for (int o = 16; o >= tpp; o >>= 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc.v[i];
+    for (int i = 0; i < 4; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], o);
+  }
+  __syncthreads();
+  if (lane < per_warp) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[(warp * per_warp + lane) * 4 + i] = acc.v[i];
+  }
   __syncthreads();
   if (tid < tpp) {
-    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = tid; t < kPwThreads; t += tpp) {
+    const int n_entries = (kPwThreads / 32) * per_warp;
+    float s[4] = {0, 0, 0, 0};
+    for (int e = tid; e < n_entries; e += tpp) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] += red[t * 8 + i];
+      for (int i = 0; i < 4; ++i) s[i] += red[e * 4 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(dst + i, s[i]);
+  }
+}
+
+// Sum `acc` over all threads of the block that share (threadIdx.x % tpp) and atomically add the result to
+// dst[8].  Stage 1: warp shuffles across the lanes with equal (lane % tpp) (tpp < 32 only); stage 2: one
+// partial per (warp, channel group) through shared memory, at most 8 partials per group are summed serially.
+// (A first version let tpp threads walk 256/tpp partials each: for C = 32 that serial tail cost more than the
+// block's whole streaming loop.)   red: shared float[kPwThreads * 8].
+__device__ __forceinline__ void block_reduce8(bf8 acc, float* red, int tpp, float* dst, float scale) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per_warp = tpp < 32 ? tpp : 32;
+  for (int o = 16; o >= tpp; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] += __shfl_xor_sync(0xffffffffu, acc.v[i], o);
+  }
+  __syncthreads();
+  if (lane < per_warp) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(warp * per_warp + lane) * 8 + i] = acc.v[i];
+  }
+  __syncthreads();
+  if (tid < tpp) {
+    const int n_entries = (kPwThreads / 32) * per_warp;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int e = tid; e < n_entries; e += tpp) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += red[e * 8 + i];
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) atomicAdd(dst + i, s[i] * scale);
@@ -98,53 +157,67 @@ __global__ void __launch_bounds__(kPwThreads)
 //   gu2 = g*lrelu'(u2) ; d_gb += sum gu2*l1 ; d_bb += sum gu2
 //   gu1 = gu2*gb*lrelu'(u1) ; d_ga += sum gu1*x ; d_ba += sum gu1
 //   gx  = gu1*ga (+ g_add) ; colsum += sum gx (optional: bias gradient of the producing conv)
-__global__ void __launch_bounds__(kPwThreads)
+__global__ void __launch_bounds__(kPwThreads, 4)
     affine2_bwd_kernel(const __nv_bfloat16* __restrict__ g_a, const __nv_bfloat16* __restrict__ x,
                        const __nv_bfloat16* __restrict__ g_add, __nv_bfloat16* __restrict__ gx,
                        const float* ga, const float* ba, const float* gb, const float* bb,
                        float* d_ga, float* d_ba, float* d_gb, float* d_bb, long long tab_stride,
                        const float* gscale, float* dot, float* colsum, int HW, int C, int pix_per_block,
                        float slope) {
-  __shared__ float red[kPwThreads * 8];
+  __shared__ float red[kPwThreads * 4];
   const int n = blockIdx.y;
-  const int tpp = C >> 3;
+  const int tpp = C >> 2;   // 4 channels per thread
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp, ppi = kPwThreads / tpp;
-  const long long t_off = n * tab_stride + cg * 8;
-  const bf8 g1 = ldf8(ga + t_off), b1 = ldf8(ba + t_off), g2 = ldf8(gb + t_off), b2 = ldf8(bb + t_off);
+  const long long t_off = n * tab_stride + cg * 4;
+  const bf4 g1 = ldf4(ga + t_off), b1 = ldf4(ba + t_off), g2 = ldf4(gb + t_off), b2 = ldf4(bb + t_off);
   const float gs = gscale ? __ldg(gscale) : 1.f;
   const long long base = static_cast<long long>(n) * HW * C;
-  bf8 a_ga{}, a_ba{}, a_gb{}, a_bb{}, a_cs{};
+  bf4 a_ga{}, a_ba{}, a_gb{}, a_bb{}, a_cs{};
   float a_dot = 0.f;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  for (int p = p0 + pl; p < p1; p += ppi) {
-    const long long off = base + static_cast<long long>(p) * C + cg * 8;
-    const bf8 gin = ld8(g_a + off), xv = ld8(x + off);
-    bf8 o;
-    if (g_add) o = ld8(g_add + off);
+  constexpr int U = 2;   // pixels in flight per thread: both batches' loads are issued before any math
+  for (int pb = p0 + pl; pb < p1; pb += U * ppi) {
+    bf4 gin[U], xv[U], o[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float u1 = fmaf(g1.v[i], xv.v[i], b1.v[i]);
-      const float l1 = lrelu(u1, slope);
-      const float u2 = fmaf(g2.v[i], l1, b2.v[i]);
-      a_dot += gin.v[i] * lrelu(u2, slope);
-      const float gu2 = gin.v[i] * gs * dlrelu(u2, slope);
-      a_gb.v[i] += gu2 * l1;
-      a_bb.v[i] += gu2;
-      const float gu1 = gu2 * g2.v[i] * dlrelu(u1, slope);
-      a_ga.v[i] += gu1 * xv.v[i];
-      a_ba.v[i] += gu1;
-      const float r = gu1 * g1.v[i] + (g_add ? o.v[i] : 0.f);
-      o.v[i] = r;
-      a_cs.v[i] += r;
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * ppi;
+      if (p < p1) {
+        const long long off = base + static_cast<long long>(p) * C + cg * 4;
+        gin[u] = ld4(g_a + off);
+        xv[u] = ld4(x + off);
+        if (g_add) o[u] = ld4(g_add + off);
+      }
     }
-    st8(gx + off, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * ppi;
+      if (p < p1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float u1 = fmaf(g1.v[i], xv[u].v[i], b1.v[i]);
+          const float l1 = lrelu(u1, slope);
+          const float u2 = fmaf(g2.v[i], l1, b2.v[i]);
+          a_dot += gin[u].v[i] * lrelu(u2, slope);
+          const float gu2 = gin[u].v[i] * gs * dlrelu(u2, slope);
+          a_gb.v[i] += gu2 * l1;
+          a_bb.v[i] += gu2;
+          const float gu1 = gu2 * g2.v[i] * dlrelu(u1, slope);
+          a_ga.v[i] += gu1 * xv[u].v[i];
+          a_ba.v[i] += gu1;
+          const float r = gu1 * g1.v[i] + (g_add ? o[u].v[i] : 0.f);
+          o[u].v[i] = r;
+          a_cs.v[i] += r;
+        }
+        st4(gx + base + static_cast<long long>(p) * C + cg * 4, o[u]);
+      }
+    }
   }
-  block_reduce8(a_ga, red, tpp, d_ga + t_off, 1.f);
-  block_reduce8(a_ba, red, tpp, d_ba + t_off, 1.f);
-  block_reduce8(a_gb, red, tpp, d_gb + t_off, 1.f);
-  block_reduce8(a_bb, red, tpp, d_bb + t_off, 1.f);
-  if (colsum) block_reduce8(a_cs, red, tpp, colsum + cg * 8, 1.f);
+  block_reduce4(a_ga, red, tpp, d_ga + t_off);
+  block_reduce4(a_ba, red, tpp, d_ba + t_off);
+  block_reduce4(a_gb, red, tpp, d_gb + t_off);
+  block_reduce4(a_bb, red, tpp, d_bb + t_off);
+  if (colsum) block_reduce4(a_cs, red, tpp, colsum + cg * 4);
   if (dot) block_reduce1(a_dot, red, dot, 1.f);
 }
 
@@ -152,7 +225,7 @@ __global__ void __launch_bounds__(kPwThreads)
 // out[n,i,j,c] = scale * sum_{a,b < f} x[n, f*i+a, f*j+b, c]  (f = 1 << shift);  colsum[c] += cs * sum x
 // avg_pool2d (discriminator/residual_block.py:27) with scale .25; backward of F.interpolate
 // (generator/model.py:40) with scale 1; shift 0 degenerates to a copy + column sum.
-__global__ void __launch_bounds__(kPwThreads)
+__global__ void __launch_bounds__(kPwThreads, 4)
     pool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, float* colsum,
                 const float* cs_dev, float cs_imm, int Ho, int Wo, int C, int shift, float scale,
                 int pix_per_block) {
@@ -168,21 +241,40 @@ __global__ void __launch_bounds__(kPwThreads)
   const int HW = Ho * Wo;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  for (int p = p0 + pl; p < p1; p += ppi) {
-    const int i = p / Wo, j = p - i * Wo;
-    bf8 s{};
-    for (int a = 0; a < f; ++a)
-      for (int b = 0; b < f; ++b) {
-        const bf8 v = ld8(x + ibase + (static_cast<long long>(f * i + a) * Wi + (f * j + b)) * C + cg * 8);
+  constexpr int U = 1;
+  for (int pb = p0 + pl; pb < p1; pb += U * ppi) {
+    bf8 v[U][4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s.v[k] += v.v[k];
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * ppi;
+      if (p < p1) {
+        const int i = p / Wo, j = p - i * Wo;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            if (a < f && b < f)
+              v[u][a * 2 + b] = ld8(x + ibase + (static_cast<long long>(f * i + a) * Wi + (f * j + b)) * C + cg * 8);
       }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc.v[k] += s.v[k];
-      s.v[k] *= scale;
     }
-    if (out) st8(out + obase + static_cast<long long>(p) * C + cg * 8, s);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * ppi;
+      if (p >= p1) continue;
+      bf8 s{};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((q >> 1) < f && (q & 1) < f) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s.v[k] += v[u][q].v[k];
+        }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc.v[k] += s.v[k];
+        s.v[k] *= scale;
+      }
+      if (out) st8(out + obase + static_cast<long long>(p) * C + cg * 8, s);
+    }
   }
   if (colsum) block_reduce8(acc, red, tpp, colsum + cg * 8, cs_imm * (cs_dev ? __ldg(cs_dev) : 1.f));
 }
@@ -190,7 +282,7 @@ __global__ void __launch_bounds__(kPwThreads)
 // ------------------------------------------------------------------------------------ D residual gate
 // y = s + gamma * r, r = lrelu(pre)  (discriminator/residual_block.py:30).  Backward wrt the residual:
 //   g_pre = g_y * gamma * lrelu'(r) ; dgamma += <g_y, r> ; colsum[c] += sum g_y (scale_conv bias grad)
-__global__ void __launch_bounds__(kPwThreads)
+__global__ void __launch_bounds__(kPwThreads, 4)
     dres_bwd_kernel(const __nv_bfloat16* __restrict__ g_y, const __nv_bfloat16* __restrict__ r,
                     __nv_bfloat16* __restrict__ g_pre, const float* gamma, float* dgamma, float* colsum,
                     int HW, int C, int pix_per_block, float slope) {
@@ -204,17 +296,32 @@ __global__ void __launch_bounds__(kPwThreads)
   float dot = 0.f;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  for (int p = p0 + pl; p < p1; p += ppi) {
-    const long long off = base + static_cast<long long>(p) * C + cg * 8;
-    const bf8 g = ld8(g_y + off), rv = ld8(r + off);
-    bf8 o;
+  constexpr int U = 2;
+  for (int pb = p0 + pl; pb < p1; pb += U * ppi) {
+    bf8 g[U], rv[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dot += g.v[i] * rv.v[i];
-      acc.v[i] += g.v[i];
-      o.v[i] = g.v[i] * gm * dlrelu(rv.v[i], slope);
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * ppi;
+      if (p < p1) {
+        const long long off = base + static_cast<long long>(p) * C + cg * 8;
+        g[u] = ld8(g_y + off);
+        rv[u] = ld8(r + off);
+      }
     }
-    st8(g_pre + off, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * ppi;
+      if (p < p1) {
+        bf8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dot += g[u].v[i] * rv[u].v[i];
+          acc.v[i] += g[u].v[i];
+          o.v[i] = g[u].v[i] * gm * dlrelu(rv[u].v[i], slope);
+        }
+        st8(g_pre + base + static_cast<long long>(p) * C + cg * 8, o);
+      }
+    }
   }
   if (colsum) block_reduce8(acc, red, tpp, colsum + cg * 8, 1.f);
   if (dgamma) block_reduce1(dot, red, dgamma, 1.f);
@@ -420,10 +527,13 @@ static inline int blocks_for(long long total, int threads) {
   return static_cast<int>((total + threads - 1) / threads);
 }
 static inline bool c_ok(int C) { return C >= 8 && C % 8 == 0 && (kPwThreads % (C / 8)) == 0; }
-// pixels per block so that the grid has roughly 8 waves of blocks over the SMs
+static inline bool c4_ok(int C) { return C >= 4 && C % 4 == 0 && C / 4 <= kPwThreads && (kPwThreads % (C / 4)) == 0; }
+// pixels per block so that the grid is ONE wave of resident blocks (4 per SM): every block ends with
+// same-address atomics (gate / bias / gamma-beta gradients), whose serialisation at L2 is the visible tail of
+// these kernels, so fewer, fatter blocks win over many short ones
 static inline int pick_ppb(int N, int HW, int C) {
   const int ppi = kPwThreads / (C / 8);
-  long long want_blocks = 8LL * num_sms();
+  long long want_blocks = 4LL * num_sms();
   long long per_n = (want_blocks + N - 1) / N;
   int ppb = static_cast<int>((HW + per_n - 1) / per_n);
   ppb = ((ppb + ppi - 1) / ppi) * ppi;
@@ -457,9 +567,9 @@ int dfgan_affine2_bwd(const void* g_a, const void* x, const void* g_add, void* g
                       const float* ba, const float* gb, const float* bb, float* d_ga, float* d_ba,
                       float* d_gb, float* d_bb, int64_t tab_stride, const float* gscale, float* dot,
                       float* colsum, int N, int HW, int C, dfgan_stream_t st) {
-  if (!g_a || !x || !gx || !ga || !ba || !gb || !bb || !d_ga || !d_ba || !d_gb || !d_bb || !c_ok(C))
+  if (!g_a || !x || !gx || !ga || !ba || !gb || !bb || !d_ga || !d_ba || !d_gb || !d_bb || !c4_ok(C))
     return DFGAN_E_ARG;
-  const int ppb = pick_ppb(N, HW, C);
+  const int ppb = pick_ppb(N, HW, 2 * C);   // C/4 threads per pixel -> 1024/C pixels per iteration
   affine2_bwd_kernel<<<dim3((HW + ppb - 1) / ppb, N), kPwThreads, 0, STREAM(st)>>>(
       static_cast<const __nv_bfloat16*>(g_a), static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(g_add), static_cast<__nv_bfloat16*>(gx), ga, ba, gb, bb, d_ga, d_ba,
