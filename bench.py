@@ -236,6 +236,64 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_side_workload(args):
+    """BASELINE configs[3] (MA-GP step, 45.51 GFLOP/img) and configs[4] (generator sampling, 15.013 GFLOP/img):
+    same harness, eager launches, device-resident inputs; one JSON line."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from gan_codes_b200.engine import DFGANTrainer
+    from gan_codes_b200.modules import Discriminator, Generator
+    torch.manual_seed(123321)
+    G, D = Generator(32, 100).to(dev), Discriminator(32).to(dev)
+    if args.workload == "gp":
+        B = (args.batch if args.batch != 32 else 64) // world
+        gflop = 45.51
+    else:
+        B = args.batch if args.batch != 32 else 256
+        gflop = 15.013
+    trainer = DFGANTrainer(G, D, B, world=world, use_graph=False)
+    gen = torch.Generator().manual_seed(5 + rank)
+    img = (torch.randn((B, 3, 256, 256), generator=gen) * 0.5).clamp_(-1, 1).to(dev)
+    sent = (torch.randn((B, 256), generator=gen) * 0.3).to(dev)
+    noise = torch.randn((B, 100), generator=gen).to(dev)
+    fn = (lambda: trainer.gp_step(img, sent)) if args.workload == "gp" else (lambda: trainer.sample(noise, sent))
+    for _ in range(max(3, args.warmup)):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        _, _, tf_sust, how = _peaks()
+        value = B * world * args.steps / (ms.item() / 1e3)
+        print(json.dumps({
+            "metric": "MA-GP discriminator step images/sec" if args.workload == "gp" else "generator sampling images/sec",
+            "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(ms.item() / args.steps, 3), "higher_is_better": True,
+            "scaling": "strong" if args.workload == "gp" else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload} 256x256 n_channels 32, batch {B}/GPU", "batch_per_gpu": B,
+                       "pct_of_bf16_peak_algorithmic": round(100 * value / world * gflop / 1e3 / tf_sust, 2),
+                       "gflop_per_image_algorithmic": gflop, "peak_source": how}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,9 +303,15 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="full", choices=["full", "gp", "sample"],
+                    help="full = headline training iteration (BASELINE configs[1]/[2]); gp = MA-GP discriminator "
+                         "update only (configs[3], default batch 64 split over the ranks); sample = no_grad generator "
+                         "forward (configs[4], default batch 256)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "full":
+        run_side_workload(args)
     else:
         run_ours(args)
 

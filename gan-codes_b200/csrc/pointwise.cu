@@ -528,12 +528,11 @@ static inline int blocks_for(long long total, int threads) {
 }
 static inline bool c_ok(int C) { return C >= 8 && C % 8 == 0 && (kPwThreads % (C / 8)) == 0; }
 static inline bool c4_ok(int C) { return C >= 4 && C % 4 == 0 && C / 4 <= kPwThreads && (kPwThreads % (C / 4)) == 0; }
-// pixels per block so that the grid is ONE wave of resident blocks (4 per SM): every block ends with
-// same-address atomics (gate / bias / gamma-beta gradients), whose serialisation at L2 is the visible tail of
-// these kernels, so fewer, fatter blocks win over many short ones
+// pixels per block so that the grid has roughly 8 blocks per SM (two waves at occupancy 4); measured better than
+// one fat wave for the backward kernels (tools/prof_pointwise.py)
 static inline int pick_ppb(int N, int HW, int C) {
   const int ppi = kPwThreads / (C / 8);
-  long long want_blocks = 4LL * num_sms();
+  long long want_blocks = 8LL * num_sms();
   long long per_n = (want_blocks + N - 1) / N;
   int ppb = static_cast<int>((HW + per_n - 1) / per_n);
   ppb = ((ppb + ppi - 1) / ppi) * ppi;
