@@ -763,6 +763,247 @@ static bool plan_halo(const dfgan_conv_desc* d, HaloK& hp, int& smem_bytes) {
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo variant of the weight gradient for the high-resolution, narrow layers (C_in, C_out <= 64).  Per
+// 16 x 8 pixel brick ONE halo tile per source view and ONE tile of the output gradient are loaded (the generic
+// kernel re-loads both once per 128-row block of (tap, ci): ~6x the TMA rows).  The pixel index is the GEMM K.
+//   A (M = 128 rows) = up to 128 / C_in filter taps that are horizontal neighbours: tap dx+1 is the same halo
+//       tile one pixel row (C_in * 2 bytes) further, i.e. the descriptor's leading-dimension offset;
+//   B (N = C_out)    = the output-gradient brick;      D[group] lives in its own TMEM columns.
+// A CTA accumulates ALL its pixel bricks (a contiguous slice of the image batch) in TMEM and adds the result
+// to the fp32 gradient once at the end.
+constexpr int kWHaloGroupsMax = 8;
+
+struct WHaloK {
+  int n_src, n_groups, slots;            // slots = 128 / C_in taps per MMA
+  int dy_min[DFGAN_MAX_SRC], dx_min[DFGAN_MAX_SRC];
+  int part_base[DFGAN_MAX_SRC];          // halo tile index of each source inside a stage (== source index)
+  int grp_src[kWHaloGroupsMax], grp_row0[kWHaloGroupsMax];   // start row of slot 0 inside the source's tile
+  int grp_tap[kWHaloGroupsMax][4];       // output tap id per slot, -1 = padding slot (rows discarded)
+  int pitch, hal_h;
+  uint32_t a_part_bytes, g_bytes, stage_bytes;
+  int n_stages;
+  int tiles_w, tiles_h, pix_tiles;
+  int Cin, Cout;
+  uint32_t idesc, tmem_cols;
+  float* dw;
+  long long s_co, s_ci, s_tap;
+  const float* scale_dev;
+  float scale_imm;
+  int ci_valid, co_valid;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+    wgrad_halo_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ WHaloK p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr uint32_t kRowA = CIN * 2u, kRowG = COUT * 2u;
+  constexpr uint32_t swz_a = (CIN == 64) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t swz_g = (COUT == 64) ? SWZ_128B : SWZ_64B;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.n_stages) * p.stage_bytes);
+  uint64_t* full = bars;        // [8]
+  uint64_t* empty = bars + 8;   // [8]
+  uint64_t* done = bars + 16;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DFGAN_MAX_SRC; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.g);
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // contiguous slice of pixel bricks for this CTA
+  const int t0 = static_cast<int>((static_cast<long long>(p.pix_tiles) * blockIdx.x) / gridDim.x);
+  const int t1 = static_cast<int>((static_cast<long long>(p.pix_tiles) * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    PipeState ps;
+    const uint32_t tx = static_cast<uint32_t>(p.n_src) * p.hal_h * p.pitch * kRowA + 128u * kRowG;
+    for (int tile = t0; tile < t1; ++tile) {
+      const int tw = tile % p.tiles_w;
+      const int r = tile / p.tiles_w;
+      const int th = r % p.tiles_h;
+      const int n = r / p.tiles_h;
+      wait_bounded(&empty[ps.stage], ps.phase ^ 1);
+      uint8_t* dst = smem + static_cast<size_t>(ps.stage) * p.stage_bytes;
+      if (leader) mbar_expect_tx(&full[ps.stage], tx);
+      for (int s = 0; s < p.n_src; ++s) {
+        if (leader)
+          tma_load_4d(dst + static_cast<size_t>(s) * p.a_part_bytes, &maps.a[s], &full[ps.stage], 0,
+                      (tw << 3) + p.dx_min[s], (th << 4) + p.dy_min[s], n);
+      }
+      if (leader)
+        tma_load_4d(dst + static_cast<size_t>(p.n_src) * p.a_part_bytes, &maps.g, &full[ps.stage], 0, tw << 3,
+                    th << 4, n);
+      __syncwarp();
+      ps.advance(p.n_stages);
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    PipeState ps;
+    const uint32_t sbo_a = static_cast<uint32_t>(p.pitch) * kRowA;   // next 8-pixel K group = next image row
+    constexpr uint32_t sbo_g = 8u * kRowG;
+    for (int tile = t0; tile < t1; ++tile) {
+      wait_bounded(&full[ps.stage], ps.phase);
+      tc_fence_after();
+      const uint32_t st_base = smem_u32(smem + static_cast<size_t>(ps.stage) * p.stage_bytes);
+      const uint32_t g_base = st_base + static_cast<uint32_t>(p.n_src) * p.a_part_bytes;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const uint32_t a0 = st_base + static_cast<uint32_t>(p.grp_src[g]) * p.a_part_bytes +
+                            static_cast<uint32_t>(p.grp_row0[g]) * kRowA;
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * COUT);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA: image rows 2k and 2k+1 of the brick
+          const uint64_t adesc = make_smem_desc(a0 + 2u * k * sbo_a, kRowA, sbo_a, swz_a);
+          const uint64_t bdesc = make_smem_desc(g_base + 2u * k * sbo_g, kRowG, sbo_g, swz_g);
+          if (leader) umma_bf16(d_tmem, adesc, bdesc, p.idesc, (tile > t0) || (k != 0));
+        }
+      }
+      if (leader) umma_commit(&empty[ps.stage]);
+      __syncwarp();
+      ps.advance(p.n_stages);
+    }
+    if (leader) umma_commit(done);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int slot = row / CIN, ci = row % CIN;
+    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+    if (t1 > t0) {
+      wait_bounded(done, 0);
+      tc_fence_after();
+      for (int g = 0; g < p.n_groups; ++g) {
+        const int tap = p.grp_tap[g][slot];
+        const bool valid = tap >= 0 && ci < p.ci_valid;
+        float* dst = p.dw + ci * p.s_ci + (tap >= 0 ? tap : 0) * p.s_tap;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g * COUT);
+#pragma unroll
+        for (int c = 0; c < COUT; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c + i < p.co_valid) atomicAdd(dst + (c + i) * p.s_co, v[i] * scale);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Plans the halo weight-gradient launch; returns false when the shape must take the generic kernel.
+static bool plan_wgrad_halo(const dfgan_wgrad_desc* d, WHaloK& k, int& smem_bytes) {
+  if ((d->Cin != 32 && d->Cin != 64) || (d->Cout != 32 && d->Cout != 64)) return false;
+  const int W = d->g.W, H = d->g.H;
+  if (W < 8 || H < 16 || static_cast<long long>(W) * H < 64 * 64) return false;
+  int dy_max[DFGAN_MAX_SRC], dx_max[DFGAN_MAX_SRC];
+  bool used[DFGAN_MAX_SRC] = {false, false, false, false};
+  for (int s = 0; s < DFGAN_MAX_SRC; ++s) k.dy_min[s] = k.dx_min[s] = dy_max[s] = dx_max[s] = 0;
+  for (int t = 0; t < d->n_taps; ++t) {
+    const int s = d->taps[t].src;
+    if (s < 0 || s >= d->n_src) return false;
+    const int dy = d->taps[t].dy, dx = d->taps[t].dx;
+    if (!used[s]) {
+      used[s] = true;
+      k.dy_min[s] = dy_max[s] = dy;
+      k.dx_min[s] = dx_max[s] = dx;
+    } else {
+      k.dy_min[s] = dy < k.dy_min[s] ? dy : k.dy_min[s];
+      dy_max[s] = dy > dy_max[s] ? dy : dy_max[s];
+      k.dx_min[s] = dx < k.dx_min[s] ? dx : k.dx_min[s];
+      dx_max[s] = dx > dx_max[s] ? dx : dx_max[s];
+    }
+  }
+  int ext_h = 0, ext_w = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    if (!used[s]) return false;
+    ext_h = dy_max[s] - k.dy_min[s] > ext_h ? dy_max[s] - k.dy_min[s] : ext_h;
+    ext_w = dx_max[s] - k.dx_min[s] > ext_w ? dx_max[s] - k.dx_min[s] : ext_w;
+  }
+  if (ext_h > 2 || ext_w > 2) return false;
+  k.slots = 128 / d->Cin;
+  k.n_src = d->n_src;
+  // groups: per source, per dy, runs of `slots` horizontally adjacent taps
+  int ng = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    k.part_base[s] = s;
+    for (int dy = k.dy_min[s]; dy <= dy_max[s]; ++dy)
+      for (int dx0 = k.dx_min[s]; dx0 <= dx_max[s]; dx0 += k.slots) {
+        int ids[4] = {-1, -1, -1, -1};
+        bool any = false;
+        for (int j = 0; j < k.slots; ++j)
+          for (int t = 0; t < d->n_taps; ++t)
+            if (d->taps[t].src == s && d->taps[t].dy == dy && d->taps[t].dx == dx0 + j) {
+              ids[j] = d->taps[t].wrow;
+              any = true;
+            }
+        if (!any) continue;
+        if (ng >= kWHaloGroupsMax) return false;
+        k.grp_src[ng] = s;
+        for (int j = 0; j < 4; ++j) k.grp_tap[ng][j] = ids[j];
+        ++ng;
+      }
+  }
+  if (ng * d->Cout > 512) return false;
+  k.n_groups = ng;
+  {
+    // padding slots read past the window: the last slot of the last run of a row reads pixel
+    // 7 + (run start) + slots - 1 relative to dx_min (runs start at multiples of `slots`)
+    const int runs = (ext_w + 1 + k.slots - 1) / k.slots;
+    const int need = 8 + runs * k.slots - 1;
+    k.pitch = need > 8 + ext_w ? need : 8 + ext_w;
+  }
+  k.hal_h = 16 + ext_h;
+  int gi = 0;
+  for (int s = 0; s < d->n_src; ++s)
+    for (int dy = k.dy_min[s]; dy <= dy_max[s]; ++dy)
+      for (int dx0 = k.dx_min[s]; dx0 <= dx_max[s]; dx0 += k.slots) {
+        if (gi < ng && k.grp_src[gi] == s) {
+          bool match = false;
+          for (int t = 0; t < d->n_taps && !match; ++t)
+            match = d->taps[t].src == s && d->taps[t].dy == dy && d->taps[t].dx >= dx0 && d->taps[t].dx < dx0 + k.slots;
+          if (!match) continue;
+          k.grp_row0[gi] = (dy - k.dy_min[s]) * k.pitch + (dx0 - k.dx_min[s]);
+          ++gi;
+        }
+      }
+  if (gi != ng) return false;
+  k.a_part_bytes = (static_cast<uint32_t>(k.hal_h * k.pitch * d->Cin * 2) + 1023u) & ~1023u;
+  k.g_bytes = (128u * d->Cout * 2u + 1023u) & ~1023u;
+  k.stage_bytes = static_cast<uint32_t>(d->n_src) * k.a_part_bytes + k.g_bytes;
+  int stages = static_cast<int>((215u * 1024u) / k.stage_bytes);
+  if (stages < 2) return false;
+  k.n_stages = stages > 8 ? 8 : stages;
+  smem_bytes = static_cast<int>(static_cast<size_t>(k.n_stages) * k.stage_bytes + 1024 + 512);
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(ng * d->Cout)) cols <<= 1;
+  k.tmem_cols = cols;
+  return true;
+}
+
 static void brick_geometry(int W, int H, int& lbw, int& lbh) {
   int bw = 1;
   while (bw < W && bw < 16) bw <<= 1;
@@ -953,6 +1194,53 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   if (d->n_src < 1 || d->n_src > DFGAN_MAX_SRC || d->n_taps < 1 || d->n_taps > DFGAN_MAX_TAPS)
     return DFGAN_E_ARG;
   if (d->Cin % 32 || d->Cout % 32 || d->g.C != d->Cout) return DFGAN_E_SHAPE;
+
+  {
+    WHaloK hk{};
+    int smem_halo = 0;
+    static const bool whalo_off = getenv("DFGAN_NO_WGRAD_HALO") != nullptr;
+    if (!whalo_off && d->k_splits == 0 && plan_wgrad_halo(d, hk, smem_halo)) {
+      WgradMaps maps{};
+      const int W = d->g.W, H = d->g.H, N = d->g.N;
+      hk.tiles_w = (W + 7) / 8, hk.tiles_h = (H + 15) / 16;
+      hk.pix_tiles = hk.tiles_w * hk.tiles_h * N;
+      hk.Cin = d->Cin, hk.Cout = d->Cout;
+      hk.idesc = make_idesc_bf16(128, d->Cout, 1, 1);
+      hk.dw = d->dw, hk.s_co = d->s_co, hk.s_ci = d->s_ci, hk.s_tap = d->s_tap;
+      hk.scale_dev = d->scale_dev, hk.scale_imm = d->scale_imm;
+      hk.ci_valid = d->ci_valid > 0 ? d->ci_valid : d->Cin;
+      hk.co_valid = d->co_valid > 0 ? d->co_valid : d->Cout;
+      for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
+        const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
+        if (v.C != d->Cin) return DFGAN_E_SHAPE;
+        int rc = make_map_nhwc(&maps.a[s], v, d->Cin, hk.pitch, hk.hal_h, 1);
+        if (rc) return rc;
+      }
+      int rc = make_map_nhwc(&maps.g, d->g, d->Cout, 8, 16, 1);
+      if (rc) return rc;
+      int grid = hk.pix_tiles < num_sms() ? hk.pix_tiles : num_sms();
+      const double pix = static_cast<double>(N) * H * W;
+      double bytes = 2.0 * pix * d->Cout + 4.0 * d->n_taps * d->Cin * d->Cout;
+      for (int s = 0; s < d->n_src; ++s)
+        bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
+      ProfileScope prof(1, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream);
+#define DFGAN_LAUNCH_WHALO(CI, CO)                                                                        \
+  do {                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<CI, CO>,                                       \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                     \
+    wgrad_halo_kernel<CI, CO><<<grid, kConvThreads, smem_halo, stream>>>(maps, hk);                       \
+  } while (0)
+      if (d->Cin == 32 && d->Cout == 32) DFGAN_LAUNCH_WHALO(32, 32);
+      else if (d->Cin == 32 && d->Cout == 64) DFGAN_LAUNCH_WHALO(32, 64);
+      else if (d->Cin == 64 && d->Cout == 32) DFGAN_LAUNCH_WHALO(64, 32);
+      else DFGAN_LAUNCH_WHALO(64, 64);
+#undef DFGAN_LAUNCH_WHALO
+      count_launch();
+      DFGAN_CUDA_CHECK_LAUNCH();
+      return DFGAN_OK;
+    }
+  }
 
   WgradK k{};
   WgradMaps maps{};

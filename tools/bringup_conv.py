@@ -431,7 +431,10 @@ def wgrad():
     from gan_codes_b200 import convops as co
     ok = True
     for (N, C, K, H, k) in [(2, 64, 64, 32, 3), (2, 32, 32, 64, 3), (4, 256, 256, 8, 3), (2, 128, 64, 32, 3),
-                            (2, 512, 512, 4, 3), (2, 32, 64, 64, 4), (2, 256, 512, 16, 4), (2, 64, 128, 32, 1)]:
+                            (2, 512, 512, 4, 3), (2, 32, 64, 64, 4), (2, 256, 512, 16, 4), (2, 64, 128, 32, 1),
+                            # high-resolution narrow layers -> wgrad_halo_kernel
+                            (2, 64, 64, 64, 3), (3, 32, 64, 96, 3), (2, 64, 32, 128, 3), (2, 32, 64, 256, 4),
+                            (2, 64, 64, 128, 4), (2, 32, 32, 128, 1), (2, 64, 32, 64, 1)]:
         x = torch.randn(N, C, H, H, device="cuda").bfloat16()
         Ho = H // 2 if k == 4 else H
         g = torch.randn(N, K, Ho, Ho, device="cuda").bfloat16()
