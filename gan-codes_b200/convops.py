@@ -84,7 +84,8 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
              addend: Optional[torch.Tensor] = None, add_shift: int = 0, add_scale: float = 1.0,
              mask_src: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, post_mode: int = 0,
              tables: Optional[tuple] = None, tab_stride: int = 0, out_nchw: Optional[torch.Tensor] = None,
-             co_valid: int = 0, tanh_out: bool = False, n_tile: int = 0, max_ctas: int = 0) -> None:
+             co_valid: int = 0, tanh_out: bool = False, n_tile: int = 0, max_ctas: int = 0,
+             phase_cout: int = 0) -> None:
     """epilogue(sum_taps src[tap] (*) wpack[tap rows]) -- see dfgan_conv_run in include/dfgan_b200.h.
 
     ``out`` / ``aux`` / ``out2`` / ``mask_src`` are NHWC bf16 tensors (possibly strided phase views) that
@@ -102,7 +103,7 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
     d.wpack, d.w_rows, d.Cin, d.Cout = wpack.data_ptr(), wpack.shape[0], wpack.shape[1], cout
     ref = next((t for t in (out, aux, out2) if t is not None), None)
     if ref is not None:
-        assert ref.dtype == torch.bfloat16 and ref.stride(3) == 1 and ref.shape[3] == cout
+        assert ref.dtype == torch.bfloat16 and ref.stride(3) == 1 and ref.shape[3] == (phase_cout or cout)
         d.out_sn, d.out_sh, d.out_sw = ref.stride(0), ref.stride(1), ref.stride(2)
         for t in (out, aux, out2, mask_src):
             if t is not None:
@@ -113,12 +114,12 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
                                               (out_nchw.shape[0], out_nchw.shape[2], out_nchw.shape[3]))
     d.N, d.H, d.W = n, h, w
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() == cout
+        assert bias.dtype == torch.float32 and bias.numel() == (phase_cout or cout)
     d.out, d.aux, d.out2, d.mask_src = _ptr(out), _ptr(aux), _ptr(out2), _ptr(mask_src)
     d.bias, d.scale_dev, d.scale_imm = _ptr(bias), _ptr(scale_dev), scale_imm
     d.lrelu_pre, d.slope = int(lrelu_pre), SLOPE
     if addend is not None:
-        assert addend.dtype == torch.bfloat16 and addend.stride(3) == 1 and addend.shape[3] == cout
+        assert addend.dtype == torch.bfloat16 and addend.stride(3) == 1 and addend.shape[3] == (phase_cout or cout)
         d.addend = addend.data_ptr()
         d.add_sn, d.add_sh, d.add_sw = addend.stride(0), addend.stride(1), addend.stride(2)
     d.add_shift, d.add_scale = add_shift, add_scale
@@ -132,6 +133,9 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
         assert tuple(out_nchw.shape) == (n, co_valid, h, w), (out_nchw.shape, (n, co_valid, h, w))
         d.out_nchw, d.co_valid, d.tanh_out = out_nchw.data_ptr(), co_valid, int(tanh_out)
     d.n_tile_hint, d.max_ctas = n_tile, max_ctas
+    if phase_cout:
+        assert grid is not None and cout == 4 * phase_cout
+    d.phase_cout = phase_cout
     _lib.check(_lib.lib().dfgan_conv_run(C.byref(d), _stream()), "dfgan_conv_run")
 
 
@@ -198,3 +202,37 @@ def taps_subpixel_wgrad(a: int, c: int) -> list:
     base = (a * 2 + c) * 4
     return [(0, dy, dx, base + yi * 2 + xi)
             for yi, (dy, _) in enumerate(SUBPIX_ROWS[a]) for xi, (dx, _) in enumerate(SUBPIX_ROWS[c])]
+
+
+# ------------------------------------------------------------------------------------ merged phases
+# One launch for the four phases of a 2x-upsampling layer: 9 input shifts (dy,dx in -1..1), weight rows
+# [shift][phase a*2+c][channel]; a (shift, phase) block is zero when the phase does not read that shift.
+def taps_merged(rows_per_phase: int) -> list:
+    return [(0, dy, dx, ((dy + 1) * 3 + (dx + 1)) * 4 * rows_per_phase) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+
+
+def subpixel_merged_slots() -> list:
+    """36 slots (shift-major, then phase) for upsample -> conv3x3 (App. C-4)."""
+    slots = []
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            for a in (0, 1):
+                for c in (0, 1):
+                    rs = dict(SUBPIX_ROWS[a]).get(dy, ())
+                    ss = dict(SUBPIX_ROWS[c]).get(dx, ())
+                    slots.append([r * 3 + s for r in rs for s in ss])
+    return slots
+
+
+def s2dgrad_merged_slots() -> list:
+    """36 slots for the data gradient of a 4x4 / stride-2 / pad-1 conv: phase (a,c) of the input grid reads
+    the output gradient at shift (dy,dx) through kernel tap (r,s)."""
+    sel = {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}}
+    slots = []
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            for a in (0, 1):
+                for c in (0, 1):
+                    r, s_ = sel[a].get(dy), sel[c].get(dx)
+                    slots.append([] if r is None or s_ is None else [r * 4 + s_])
+    return slots

@@ -54,6 +54,7 @@ struct ConvK {
   long long tab_stride;
   float* out_nchw;  // fp32 [N][co_valid][H][W] store (image boundary), optional tanh
   int co_valid, tanh_out;
+  int phase_cout;   // > 0: columns are 4 output phases x phase_cout channels of a 2x-upsampled output grid
 };
 
 __device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -292,7 +293,15 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         float v[16];
         tmem_ld16(taddr + c, v);
         const int col = nt * p.n_tile + c;
-        if (valid && col < p.Cout) epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale);
+        if (valid && col < p.Cout) {
+          if (p.phase_cout) {
+            const int ph = col / p.phase_cout;
+            const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
+            epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale);
+          } else {
+            epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -687,7 +696,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         for (int c = 0; c < p.n_tile; c += 16) {
           float v[16];
           tmem_ld16(taddr + c, v);
-          if (valid) epilogue_chunk(p, v, c, n, h, w, o_off, a_off, scale);
+          if (valid) {
+            if (p.phase_cout) {
+              const int ph = c / p.phase_cout;
+              const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
+              epilogue_chunk(p, v, c - ph * p.phase_cout, n, h, w, oo, a_off, scale);
+            } else {
+              epilogue_chunk(p, v, c, n, h, w, o_off, a_off, scale);
+            }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -1038,6 +1055,7 @@ static void fill_epilogue(ConvK& k, const dfgan_conv_desc* d) {
   k.tab_ga = d->tab_ga, k.tab_ba = d->tab_ba, k.tab_gb = d->tab_gb, k.tab_bb = d->tab_bb;
   k.tab_stride = d->tab_stride;
   k.out_nchw = d->out_nchw, k.co_valid = d->co_valid, k.tanh_out = d->tanh_out;
+  k.phase_cout = d->phase_cout;
 }
 
 // executed work of a launch: real output pixels x Cout x (taps * Cin) MACs; bytes = every source view read once
@@ -1060,6 +1078,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   if (d->post_mode < 0 || d->post_mode > 2 || (d->post_mode && !d->out2)) return DFGAN_E_ARG;
   if (d->post_mode == 2 && !(d->tab_ga && d->tab_ba && d->tab_gb && d->tab_bb)) return DFGAN_E_ARG;
   if (d->out_nchw && (d->co_valid < 1 || d->co_valid > d->Cout)) return DFGAN_E_ARG;
+  if (d->phase_cout && (d->phase_cout % 16 || d->Cout != 4 * d->phase_cout || d->out_nchw)) return DFGAN_E_ARG;
   if (d->n_src < 1 || d->n_src > DFGAN_MAX_SRC || d->n_taps < 1 || d->n_taps > DFGAN_MAX_TAPS)
     return DFGAN_E_ARG;
   if (d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1) return DFGAN_E_SHAPE;

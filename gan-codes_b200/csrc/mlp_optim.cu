@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kLinThreads)
 }
 
 // ------------------------------------------------------------------------------------ weight packing
+constexpr int kPackSlots = 36;   // 9 shifts x 4 output phases of the merged sub-pixel operands
 struct PackP {
   const float* w;  // [Co][Ci][kh*kw] fp32
   __nv_bfloat16* out;
@@ -122,7 +123,7 @@ struct PackP {
   int transpose;  // 0: rows = co, cols = ci ; 1: rows = ci, cols = co
   int rows_pad, cols_pad, n_slots;
   float scale;
-  int8_t taps[16][4];  // per slot: source tap indices summed (-1 = unused)
+  int8_t taps[kPackSlots][4];  // per slot: source tap indices summed (-1 = unused)
 };
 __global__ void pack_kernel(const __grid_constant__ PackP p) {
   const long long total = static_cast<long long>(p.n_slots) * p.rows_pad * p.cols_pad;
@@ -266,13 +267,13 @@ int dfgan_linear_batched(const dfgan_linear_item* items_dev, int n_items, int B,
 int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int transpose, int rows_pad,
                        int cols_pad, int n_slots, const int8_t* slot_taps /* host [n_slots][4] */,
                        float scale, dfgan_stream_t st) {
-  if (!w || !out || !slot_taps || n_slots < 1 || n_slots > 16) return DFGAN_E_ARG;
+  if (!w || !out || !slot_taps || n_slots < 1 || n_slots > kPackSlots) return DFGAN_E_ARG;
   if (rows_pad < (transpose ? Ci : Co) || cols_pad < (transpose ? Co : Ci)) return DFGAN_E_SHAPE;
   PackP p{};
   p.w = w, p.out = static_cast<__nv_bfloat16*>(out);
   p.Co = Co, p.Ci = Ci, p.KK = KK, p.transpose = transpose;
   p.rows_pad = rows_pad, p.cols_pad = cols_pad, p.n_slots = n_slots, p.scale = scale;
-  for (int s = 0; s < 16; ++s)
+  for (int s = 0; s < kPackSlots; ++s)
     for (int j = 0; j < 4; ++j) p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
   const long long total = static_cast<long long>(n_slots) * rows_pad * cols_pad;
   pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, STREAM(st)>>>(p);
@@ -288,13 +289,13 @@ int dfgan_pack_entry_size(void) { return static_cast<int>(sizeof(PackEntry)); }
 int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, int Ci, int KK, int transpose,
                           int rows_pad, int cols_pad, int n_slots, const int8_t* slot_taps, float scale,
                           int block_start) {
-  if (!entry_out || !w || !out || !slot_taps || n_slots < 1 || n_slots > 16) return DFGAN_E_ARG;
+  if (!entry_out || !w || !out || !slot_taps || n_slots < 1 || n_slots > kPackSlots) return DFGAN_E_ARG;
   if (rows_pad < (transpose ? Ci : Co) || cols_pad < (transpose ? Co : Ci)) return DFGAN_E_SHAPE;
   PackEntry e{};
   e.p.w = w, e.p.out = static_cast<__nv_bfloat16*>(out);
   e.p.Co = Co, e.p.Ci = Ci, e.p.KK = KK, e.p.transpose = transpose;
   e.p.rows_pad = rows_pad, e.p.cols_pad = cols_pad, e.p.n_slots = n_slots, e.p.scale = scale;
-  for (int s = 0; s < 16; ++s)
+  for (int s = 0; s < kPackSlots; ++s)
     for (int j = 0; j < 4; ++j) e.p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
   e.block_start = block_start;
   *static_cast<PackEntry*>(entry_out) = e;

@@ -18,6 +18,7 @@ from . import kernels as K
 
 BF16, F32 = torch.bfloat16, torch.float32
 SENT_DIM = 256
+MERGE_MAX = 64   # see gnet.MERGE_MAX
 
 
 def d_plan(params: Dict[str, torch.Tensor]) -> List[tuple]:
@@ -49,7 +50,8 @@ class DPacked:
         self.w0_f, self.w0_d = e(32, 32), e(9 * 16, 32)
         self.blocks = []
         for (_, cin, cout, sc) in self.plan:
-            self.blocks.append(dict(w4_f=e(16 * cout, cin), w4_d=e(16 * cin, cout), w3_f=e(9 * cout, cout),
+            self.blocks.append(dict(w4_f=e(16 * cout, cin), w4_d=e((36 if cin <= MERGE_MAX else 16) * cin, cout),
+                                    w3_f=e(9 * cout, cout),
                                     w3_d=e(9 * cout, cout), ws_f=e(cout, cin) if sc else None,
                                     ws_d=e(cin, cout) if sc else None))
         wh = params["img_sentence_forward.0.weight"]
@@ -65,7 +67,7 @@ class DPacked:
         for (p, cin, cout, sc), b in zip(self.plan, self.blocks):
             w4, w3 = params[p + ".residual_conv.0.weight"], params[p + ".residual_conv.2.weight"]
             pp.add(w4, b["w4_f"])
-            pp.add(w4, b["w4_d"], transpose=True)
+            pp.add(w4, b["w4_d"], transpose=True, slots=co.s2dgrad_merged_slots() if cin <= MERGE_MAX else None)
             pp.add(w3, b["w3_f"])
             pp.add(w3, b["w3_d"], transpose=True)
             if sc:
@@ -154,10 +156,15 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
         else:
             g_s = g_y
         g_x = e(n, 2 * h, 2 * w, cin)
-        for a in (0, 1):
-            for c in (0, 1):
-                co.conv_run([g_c1], co.taps_4x4s2_dgrad(cin, a, c), b["w4_d"], cin, g_x[:, a::2, c::2, :],
-                            addend=g_s, add_scale=0.25)
+        if cin <= MERGE_MAX:
+            # data gradient of the stride-2 conv: the four input phases in one launch (9 shifts, N = 4*cin)
+            co.conv_run([g_c1], co.taps_merged(cin), b["w4_d"], 4 * cin, g_x, grid=(n, h, w), addend=g_s,
+                        add_scale=0.25, phase_cout=cin)
+        else:
+            for a in (0, 1):
+                for c in (0, 1):
+                    co.conv_run([g_c1], co.taps_4x4s2_dgrad(cin, a, c), b["w4_d"], cin, g_x[:, a::2, c::2, :],
+                                addend=g_s, add_scale=0.25)
         if grads is not None:
             w3, w4 = params[p + ".residual_conv.2.weight"], params[p + ".residual_conv.0.weight"]
             co.wgrad_run([c1], TAPS3_ID, g_c2, grads[p + ".residual_conv.2.weight"], _oihw_strides(w3))

@@ -18,6 +18,7 @@ from .dnet import TAPS3_ID, _oihw_strides
 
 BF16, F32 = torch.bfloat16, torch.float32
 SENT_DIM, HID = 256, 256
+MERGE_MAX = 64   # widest phase (channels) for which the merged 9-shift launch beats four 4-tap launches
 MLPS = [(fb, m) for fb in (1, 2, 3, 4) for m in ("gamma_mlp", "beta_mlp")]
 
 
@@ -50,7 +51,10 @@ class GPacked:
             if c1 % 32 or c2 % 32:
                 raise ValueError("channel counts must be multiples of 32 (n_channels % 32 == 0)")
             taps1 = 9 if i == 0 else 16
-            self.blocks.append(dict(w1_f=e(taps1 * c2, c1), w1_d=e(taps1 * c1, c2), w2_f=e(9 * c2, c2),
+            # up-blocks: the four sub-pixel phases run as ONE launch over 9 shifts when 4*c2 <= 256 (an MMA costs
+            # the same for any N <= 256, so the zero blocks are free); wider layers keep four 4-tap launches
+            n1 = 9 if i == 0 else (36 if c2 <= MERGE_MAX else 16)
+            self.blocks.append(dict(w1_f=e(n1 * c2, c1), w1_d=e(taps1 * c1, c2), w2_f=e(9 * c2, c2),
                                     w2_d=e(9 * c2, c2), ws_f=e(c2, c1) if sc else None,
                                     ws_d=e(c1, c2) if sc else None))
         self.c_last = self.plan[-1][2]
@@ -64,7 +68,8 @@ class GPacked:
         slots = co.subpixel_slots()
         for i, ((p, c1, c2, sc), b) in enumerate(zip(self.plan, self.blocks)):
             w1, w2 = params[p + ".conv_1.weight"], params[p + ".conv_2.weight"]
-            pp.add(w1, b["w1_f"], slots=None if i == 0 else slots)
+            pp.add(w1, b["w1_f"], slots=None if i == 0 else
+                   (co.subpixel_merged_slots() if c2 <= MERGE_MAX else slots))
             pp.add(w1, b["w1_d"], transpose=True, slots=None if i == 0 else slots)
             pp.add(w2, b["w2_f"])
             pp.add(w2, b["w2_d"], transpose=True)
@@ -196,7 +201,11 @@ def generator_forward(pk: GPacked, params, mlp: GMlp, noise: torch.Tensor, sent:
             s = z
         h1, a34 = e(n, hh, hh, c2), e(n, hh, hh, c2)
         t34 = mlp.tables(p, 3)
-        if up:
+        if up and c2 <= MERGE_MAX:   # all four sub-pixel phases in one launch (9 shifts, N = 4*c2)
+            co.conv_run([a12], co.taps_merged(c2), b["w1_f"], 4 * c2, None, grid=(n, h, h),
+                        bias=params[p + ".conv_1.bias"], aux=h1, out2=a34, post_mode=2, tables=t34,
+                        tab_stride=mlp.T, phase_cout=c2)
+        elif up:
             for a in (0, 1):
                 for c in (0, 1):
                     co.conv_run([a12], co.taps_subpixel_fwd(c2, a, c), b["w1_f"], c2, None, grid=(n, h, h),

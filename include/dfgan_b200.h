@@ -57,6 +57,9 @@ typedef struct dfgan_tap {
  *   out2[n,h,w,co] = post(bf16(v))            (optional, out strides); post_mode 1: leaky_relu,
  *        2: leaky_relu(gb*leaky_relu(ga*v+ba)+bb) with ga.. = tab_*[n*tab_stride + co]  (AffineBlock pair)
  * At least one of out / aux / out2 / out_nchw must be given.
+ * phase_cout > 0 merges the four phase convolutions of a 2x-upsampling layer (upsample->conv3x3, and the data gradient
+ * of a 4x4 stride-2 conv) into ONE launch over the 9 distinct input shifts: N = 4*phase_cout, zero weight blocks where
+ * a phase does not use a shift -- an MMA costs the same for any N <= 256, so this is 9 instead of 16 MMA groups.
  * replaces: nn.Conv2d forward and the data-gradient half of aten::convolution_backward at
  *   generator/residual_block.py:16,21,25,40,47  discriminator/residual_block.py:11,13,19
  *   discriminator/model.py:31 ; the stride-2 conv is expressed with four parity views of the input,
@@ -93,6 +96,8 @@ typedef struct dfgan_conv_desc {
   int64_t tab_stride;
   float* out_nchw;
   int32_t co_valid, tanh_out;
+  int32_t phase_cout; /* > 0: Cout == 4*phase_cout; column block p=(a,c) is written to pixel (2h+a, 2w+c) of the
+                         outputs (merged sub-pixel phases), bias / tables / addend are indexed by co % phase_cout */
 } dfgan_conv_desc;
 
 int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream);

@@ -194,6 +194,38 @@ def subpixel():
 
 
 @case
+def merged():
+    """Merged-phase launches: upsample->conv3x3 forward and the 4x4/stride-2 data gradient as ONE conv over 9 shifts."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co
+    ok = True
+    for (N, C, Kc, H) in [(2, 64, 32, 64), (2, 256, 128, 16), (3, 128, 64, 32), (2, 256, 256, 8)]:
+        x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        w = (torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5))
+        b = torch.randn(Kc, device="cuda")
+        ref = F.conv2d(F.interpolate(x.float(), scale_factor=2), w, b, padding=1)
+        wm = _pack(w, slots=co.subpixel_merged_slots())
+        out = torch.empty(N, 2 * H, 2 * H, Kc, device="cuda", dtype=torch.bfloat16)
+        co.conv_run([_nhwc(x)], co.taps_merged(Kc), wm, 4 * Kc, out, grid=(N, H, H), bias=b, phase_cout=Kc)
+        # stride-2 data gradient: g on the HxH grid, dx on the 2Hx2H grid, plus the pooled-shortcut addend
+        w4 = (torch.randn(C, Kc, 4, 4, device="cuda") / (4 * Kc ** 0.5)).bfloat16()     # conv Kc -> C, dgrad C -> Kc
+        g = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        add = torch.randn(N, H, H, Kc, device="cuda").bfloat16()
+        gref = F.conv_transpose2d(g.float(), w4.float(), stride=2, padding=1) + \
+            0.25 * F.interpolate(add.float().permute(0, 3, 1, 2), scale_factor=2)
+        wd = _pack(w4, True, slots=co.s2dgrad_merged_slots())
+        gx = torch.empty(N, 2 * H, 2 * H, Kc, device="cuda", dtype=torch.bfloat16)
+        co.conv_run([_nhwc(g)], co.taps_merged(Kc), wd, 4 * Kc, gx, grid=(N, H, H), addend=add, add_scale=0.25,
+                    phase_cout=Kc)
+        torch.cuda.synchronize()
+        e = (_rel(out.permute(0, 3, 1, 2), ref), _rel(gx.permute(0, 3, 1, 2), gref))
+        print(f"merged N{N} C{C} K{Kc} {H}: subpixel fwd {e[0]:.3e} s2 dgrad {e[1]:.3e}")
+        ok &= max(e) < 8e-3
+    return ok
+
+
+@case
 def edge():
     """image-boundary convs: stem via im2col (fwd / wgrad / dgrad to fp32 NCHW) and conv_out (+tanh)."""
     torch = _setup()
