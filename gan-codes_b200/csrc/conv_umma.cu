@@ -537,13 +537,14 @@ struct HaloK {
   int n_acc;                   // TMEM accumulator stages (2 or 4)
   int n_a_stages;              // halo tiles in flight (TMA latency ~2 us: 2 is not enough)
   int use_bo;
+  uint32_t a_tap_off16[DFGAN_MAX_TAPS];   // (halo-tile part + start row of the tap) >> 4, precomputed on the host
 };
 
 __device__ __forceinline__ uint64_t with_base_offset(uint64_t desc, uint32_t saddr) {
   return desc | (static_cast<uint64_t>((saddr >> 7) & 7u) << 49);
 }
 
-template <int CIN>
+template <int CIN, int NT>
 __global__ void __launch_bounds__(kHaloThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p,
                      const __grid_constant__ HaloK hp) {
@@ -632,27 +633,37 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     int stage = 0, acc = 0;
     uint32_t phase = 0, aphase = 0;
     wait_bounded(bfull, 0);
-    const uint32_t b_base = smem_u32(sB);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, sbo_b, swz);
+    const uint64_t b_step16 = hp.b_tap_bytes >> 4;
+    const bool leader = elect_one();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       wait_bounded(&tempty[acc], aphase ^ 1);
       wait_bounded(&full[stage], phase);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
       const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * a_stage_bytes);
-      const bool leader = elect_one();
-      for (int t = 0; t < p.n_taps; ++t) {
-        const int s = p.tap_src[t];
-        const int ddx = p.tap_dx[t] - hp.dx_min[s], ddy = p.tap_dy[t] - hp.dy_min[s];
-        const int part = hp.part_base[s] + (hp.mode == 0 ? ddx : 0);
-        const int row0 = ddy * hp.pitch + (hp.mode == 0 ? 0 : ddx);
-        const uint32_t a_tap = a_base + static_cast<uint32_t>(part) * hp.a_part_bytes +
-                               static_cast<uint32_t>(row0) * kRowBytes;
-        uint64_t adesc = make_smem_desc(a_tap, 16, sbo_a, swz);
-        if (hp.use_bo) adesc = with_base_offset(adesc, a_tap);
-        const uint64_t bdesc = make_smem_desc(b_base + static_cast<uint32_t>(t) * hp.b_tap_bytes, 16, sbo_b, swz);
+      // The issue loop must stay a handful of uniform-datapath instructions per MMA (an N=32 MMA is ~40 cycles,
+      // tools/ubench/mma_cost.cu): tap offsets come precomputed from the host, the tap loop is unrolled at
+      // compile time (NT) so they are constant-bank immediates.
+      const uint64_t adesc0 = make_smem_desc(a_base, 16, sbo_a, swz);
+      if (NT > 0) {
 #pragma unroll
-        for (int k = 0; k < CIN / 16; ++k) {
-          if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+        for (int t = 0; t < NT; ++t) {
+          const uint64_t adesc = adesc0 + hp.a_tap_off16[t];
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(t) * b_step16;
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k) {
+            if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+          }
+        }
+      } else {
+        for (int t = 0; t < p.n_taps; ++t) {
+          const uint64_t adesc = adesc0 + hp.a_tap_off16[t];
+          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(t) * b_step16;
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k) {
+            if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+          }
         }
       }
       if (leader) {
@@ -769,7 +780,7 @@ static bool plan_halo(const dfgan_conv_desc* d, HaloK& hp, int& smem_bytes) {
   hp.a_part_bytes = (static_cast<uint32_t>(hp.hal_h * hp.pitch * d->Cin * 2) + 1023u) & ~1023u;
   hp.b_tap_bytes = static_cast<uint32_t>(d->Cout) * d->Cin * 2u;
   hp.n_acc = 4;
-  hp.use_bo = getenv("DFGAN_HALO_BO") != nullptr && hp.mode != 0;
+  hp.use_bo = 0;
   const size_t fixed = static_cast<size_t>(d->n_taps) * hp.b_tap_bytes + 1024 + 512;
   const size_t per_stage = static_cast<size_t>(total) * hp.a_part_bytes;
   const size_t cap = 220 * 1024;
@@ -777,6 +788,13 @@ static bool plan_halo(const dfgan_conv_desc* d, HaloK& hp, int& smem_bytes) {
   int stages = static_cast<int>((cap - fixed) / per_stage);
   hp.n_a_stages = stages > 8 ? 8 : stages;
   smem_bytes = static_cast<int>(fixed + hp.n_a_stages * per_stage);
+  for (int t = 0; t < d->n_taps; ++t) {
+    const int s = d->taps[t].src;
+    const int ddx = d->taps[t].dx - hp.dx_min[s], ddy = d->taps[t].dy - hp.dy_min[s];
+    const uint32_t part = static_cast<uint32_t>(hp.part_base[s] + (hp.mode == 0 ? ddx : 0));
+    const uint32_t row0 = static_cast<uint32_t>(ddy * hp.pitch + (hp.mode == 0 ? 0 : ddx));
+    hp.a_tap_off16[t] = (part * hp.a_part_bytes + row0 * static_cast<uint32_t>(d->Cin) * 2u) >> 4;
+  }
   return true;
 }
 
@@ -796,6 +814,7 @@ struct WHaloK {
   int dy_min[DFGAN_MAX_SRC], dx_min[DFGAN_MAX_SRC];
   int part_base[DFGAN_MAX_SRC];          // halo tile index of each source inside a stage (== source index)
   int grp_src[kWHaloGroupsMax], grp_row0[kWHaloGroupsMax];   // start row of slot 0 inside the source's tile
+  uint32_t grp_off16[kWHaloGroupsMax];                      // (source tile + start row) >> 4, precomputed
   int grp_tap[kWHaloGroupsMax][4];       // output tap id per slot, -1 = padding slot (rows discarded)
   int pitch, hal_h;
   uint32_t a_part_bytes, g_bytes, stage_bytes;
@@ -878,20 +897,28 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     PipeState ps;
     const uint32_t sbo_a = static_cast<uint32_t>(p.pitch) * kRowA;   // next 8-pixel K group = next image row
     constexpr uint32_t sbo_g = 8u * kRowG;
+    const uint64_t a_kstep16 = (2u * sbo_a) >> 4;
+    constexpr uint64_t g_kstep16 = (2u * sbo_g) >> 4;
     for (int tile = t0; tile < t1; ++tile) {
       wait_bounded(&full[ps.stage], ps.phase);
       tc_fence_after();
       const uint32_t st_base = smem_u32(smem + static_cast<size_t>(ps.stage) * p.stage_bytes);
       const uint32_t g_base = st_base + static_cast<uint32_t>(p.n_src) * p.a_part_bytes;
-      for (int g = 0; g < p.n_groups; ++g) {
-        const uint32_t a0 = st_base + static_cast<uint32_t>(p.grp_src[g]) * p.a_part_bytes +
-                            static_cast<uint32_t>(p.grp_row0[g]) * kRowA;
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * COUT);
+      // a handful of uniform instructions per MMA: group offsets are host-precomputed, both loops unrolled
+      const uint64_t adesc0 = make_smem_desc(st_base, kRowA, sbo_a, swz_a);
+      const uint64_t bdesc0 = make_smem_desc(g_base, kRowG, sbo_g, swz_g);
+      const uint32_t acc_flag = tile > t0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA: image rows 2k and 2k+1 of the brick
-          const uint64_t adesc = make_smem_desc(a0 + 2u * k * sbo_a, kRowA, sbo_a, swz_a);
-          const uint64_t bdesc = make_smem_desc(g_base + 2u * k * sbo_g, kRowG, sbo_g, swz_g);
-          if (leader) umma_bf16(d_tmem, adesc, bdesc, p.idesc, (tile > t0) || (k != 0));
+      for (int g = 0; g < kWHaloGroupsMax; ++g) {
+        if (g < p.n_groups) {
+          const uint64_t ag = adesc0 + p.grp_off16[g];
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * COUT);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA: image rows 2k and 2k+1 of the brick
+            if (leader)
+              umma_bf16(d_tmem, ag + static_cast<uint64_t>(k) * a_kstep16, bdesc0 + static_cast<uint64_t>(k) * g_kstep16,
+                        p.idesc, acc_flag | (k != 0));
+          }
         }
       }
       if (leader) umma_commit(&empty[ps.stage]);
@@ -1009,6 +1036,9 @@ static bool plan_wgrad_halo(const dfgan_wgrad_desc* d, WHaloK& k, int& smem_byte
       }
   if (gi != ng) return false;
   k.a_part_bytes = (static_cast<uint32_t>(k.hal_h * k.pitch * d->Cin * 2) + 1023u) & ~1023u;
+  for (int g = 0; g < ng; ++g)
+    k.grp_off16[g] = (static_cast<uint32_t>(k.grp_src[g]) * k.a_part_bytes +
+                      static_cast<uint32_t>(k.grp_row0[g]) * static_cast<uint32_t>(d->Cin) * 2u) >> 4;
   k.g_bytes = (128u * d->Cout * 2u + 1023u) & ~1023u;
   k.stage_bytes = static_cast<uint32_t>(d->n_src) * k.a_part_bytes + k.g_bytes;
   int stages = static_cast<int>((215u * 1024u) / k.stage_bytes);
@@ -1115,16 +1145,27 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       if (grid > cap) grid = cap;
       const double pix = static_cast<double>(d->N) * d->H * d->W;
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, launch_bytes(d), stream);
-      cudaError_t e;
-      if (d->Cin == 64) {
-        e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        conv_halo_kernel<64><<<grid, kHaloThreads, smem_halo, stream>>>(maps, k, hp);
-      } else {
-        e = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        conv_halo_kernel<32><<<grid, kHaloThreads, smem_halo, stream>>>(maps, k, hp);
-      }
+#define DFGAN_LAUNCH_HALO(CI, NTAPS)                                                                      \
+  do {                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, NTAPS>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                     \
+    conv_halo_kernel<CI, NTAPS><<<grid, kHaloThreads, smem_halo, stream>>>(maps, k, hp);                  \
+  } while (0)
+#define DFGAN_LAUNCH_HALO_C(CI)                                                                           \
+  do {                                                                                                    \
+    switch (d->n_taps) {                                                                                  \
+      case 1: DFGAN_LAUNCH_HALO(CI, 1); break;                                                            \
+      case 4: DFGAN_LAUNCH_HALO(CI, 4); break;                                                            \
+      case 9: DFGAN_LAUNCH_HALO(CI, 9); break;                                                            \
+      case 16: DFGAN_LAUNCH_HALO(CI, 16); break;                                                          \
+      default: DFGAN_LAUNCH_HALO(CI, 0); break;                                                           \
+    }                                                                                                     \
+  } while (0)
+      if (d->Cin == 64) DFGAN_LAUNCH_HALO_C(64);
+      else DFGAN_LAUNCH_HALO_C(32);
+#undef DFGAN_LAUNCH_HALO_C
+#undef DFGAN_LAUNCH_HALO
       count_launch();
       DFGAN_CUDA_CHECK_LAUNCH();
       return DFGAN_OK;
