@@ -41,7 +41,7 @@ class ConvDesc(C.Structure):
         ("out2", C.c_void_p), ("post_mode", C.c_int32),
         ("tab_ga", C.c_void_p), ("tab_ba", C.c_void_p), ("tab_gb", C.c_void_p), ("tab_bb", C.c_void_p),
         ("tab_stride", C.c_int64), ("out_nchw", C.c_void_p), ("co_valid", C.c_int32), ("tanh_out", C.c_int32),
-        ("phase_cout", C.c_int32),
+        ("wpack_img", C.c_void_p), ("img_rows_per_slot", C.c_int32), ("phase_cout", C.c_int32),
     ]
 
 

@@ -37,8 +37,8 @@ _TABLE: dict = {
     "dfgan_head_out": [P, P, P, I, I, P],
     "dfgan_head_out_bwd": [P, P, P, P, P, P, I, I, P],
     "dfgan_linear_batched": [P, I, I, I, I, I, P],
-    "dfgan_pack_weights": [P, P, I, I, I, I, I, I, I, P, F, P],
-    "dfgan_pack_entry_fill": [P, P, P, I, I, I, I, I, I, I, P, F, I],
+    "dfgan_pack_weights": [P, P, I, I, I, I, I, I, I, P, F, I, P],
+    "dfgan_pack_entry_fill": [P, P, P, I, I, I, I, I, I, I, P, F, I, I],
     "dfgan_pack_batched": [P, I, I, P],
     "dfgan_unfold_subpixel_wgrad": [P, P, I, I, P],
     "dfgan_sqnorm": [P, L, P, P],

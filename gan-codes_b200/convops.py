@@ -19,6 +19,14 @@ from ._lib import ConvDesc, Tap, View4, WgradDesc
 
 SLOPE = 0.2
 
+# packed operand (data_ptr) -> (the same operand in the swizzled shared-memory image layout, rows per image slot);
+# registered by the packers for C_in % 64 == 0, C_in >= 128 and picked up by conv_run for the wide-layer halo kernel
+IMAGE_OF: dict = {}
+
+
+def register_image(wpack: torch.Tensor, wimg: torch.Tensor, rows_per_slot: int) -> None:
+    IMAGE_OF[wpack.data_ptr()] = (wimg, rows_per_slot)
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -136,6 +144,9 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
     if phase_cout:
         assert grid is not None and cout == 4 * phase_cout
     d.phase_cout = phase_cout
+    img = IMAGE_OF.get(wpack.data_ptr())
+    if img is not None:
+        d.wpack_img, d.img_rows_per_slot = img[0].data_ptr(), img[1]
     _lib.check(_lib.lib().dfgan_conv_run(C.byref(d), _stream()), "dfgan_conv_run")
 
 

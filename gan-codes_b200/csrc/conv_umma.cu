@@ -92,6 +92,15 @@ __device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* src, float* v)
 #pragma unroll
   for (int i = 0; i < 8; ++i) unpack_bf16x2(u[i], v[2 * i], v[2 * i + 1]);
 }
+// 16 consecutive fp32 (64-byte aligned: bias vectors and gamma/beta table rows at 16-column chunks)
+__device__ __forceinline__ void load_f32x16(const float* src, float* v) {
+  const float4* sp = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = __ldg(sp + i);
+    v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
+  }
+}
 __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
@@ -100,8 +109,10 @@ __device__ __forceinline__ float round_bf16(float x) {
 __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], int col, int n, int h, int w,
                                                long long o_off, long long a_off, float scale) {
     if (p.bias) {
+      float b[16];
+      load_f32x16(p.bias + col, b);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + col + i);
+      for (int i = 0; i < 16; ++i) v[i] += b[i];
     }
     if (p.lrelu_pre) {
 #pragma unroll
@@ -146,11 +157,15 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
       for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
       if (p.post_mode == 2) {
         const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
+        float ga[16], ba[16];
+        load_f32x16(p.tab_ga + t_off, ga);
+        load_f32x16(p.tab_ba + t_off, ba);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float u = lrelu(fmaf(__ldg(p.tab_ga + t_off + i), v[i], __ldg(p.tab_ba + t_off + i)), p.slope);
-          v[i] = fmaf(__ldg(p.tab_gb + t_off + i), u, __ldg(p.tab_bb + t_off + i));
-        }
+        for (int i = 0; i < 16; ++i) v[i] = lrelu(fmaf(ga[i], v[i], ba[i]), p.slope);
+        load_f32x16(p.tab_gb + t_off, ga);
+        load_f32x16(p.tab_bb + t_off, ba);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(ga[i], v[i], ba[i]);
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
@@ -1051,6 +1066,245 @@ static bool plan_wgrad_halo(const dfgan_wgrad_desc* d, WHaloK& k, int& smem_byte
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo variant for the WIDE layers (C_in a multiple of 64, >= 128) at >= 16x8 output grids.  The generic kernel
+// is bound by the TMA engine (one box row per ~4.5 cycles: 128 A rows + n_tile B rows per k-iteration against
+// 4 MMAs of n_tile/2 cycles).  Here, per 64-channel chunk,
+//   * the A brick + halo is ONE tensor load per source view (180 rows for all 9 taps instead of 9 x 128);
+//   * the B tile of every tap is ONE linear bulk copy (cp.async.bulk) from weights pre-packed as the swizzled
+//     shared-memory image (dfgan_pack_weights image=1) -- no per-row cost at all.
+// Two rings: A (halo tiles, one per chunk) and B (weight tiles, one per chunk and tap).
+struct Halo2K {
+  int dy_min[DFGAN_MAX_SRC], dx_min[DFGAN_MAX_SRC];
+  int n_src, pitch, hal_h, n_chunks;
+  uint32_t a_part_bytes, a_stage_bytes, b_bytes;
+  int n_a_stages, n_b_stages, n_acc;
+  uint32_t a_tap_off16[DFGAN_MAX_TAPS];
+  long long w_tap_stride, w_chunk_stride;   // bytes between taps / 64-channel chunks of the packed image
+  const uint8_t* wimg;
+};
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+    conv_halo2_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p,
+                      const __grid_constant__ Halo2K hp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + static_cast<size_t>(hp.n_a_stages) * hp.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + static_cast<size_t>(hp.n_b_stages) * hp.b_bytes);
+  uint64_t* fullA = bars;          // [4]
+  uint64_t* emptyA = bars + 4;     // [4]
+  uint64_t* fullB = bars + 8;      // [8]
+  uint64_t* emptyB = bars + 16;    // [8]
+  uint64_t* tfull = bars + 24;     // [4]
+  uint64_t* tempty = bars + 28;    // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = hp.n_acc * p.n_tile <= 128 ? 128u : (hp.n_acc * p.n_tile <= 256 ? 256u : 512u);
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DFGAN_MAX_SRC; ++i) tma_prefetch_desc(&maps.a[i]);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&fullA[i], 1);
+      mbar_init(&emptyA[i], 1);
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&fullB[i], 1);
+      mbar_init(&emptyB[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    const bool leader = elect_one();
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    const uint32_t txa = static_cast<uint32_t>(hp.n_src) * hp.hal_h * hp.pitch * 128u;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int n = mt / p.tiles_h;
+      const uint8_t* wbase = hp.wimg + static_cast<long long>(nt) * p.n_tile * 128;
+      for (int c = 0; c < hp.n_chunks; ++c) {
+        wait_bounded(&emptyA[sa], pa ^ 1);
+        if (leader) mbar_expect_tx(&fullA[sa], txa);
+        uint8_t* dst = sA + static_cast<size_t>(sa) * hp.a_stage_bytes;
+        for (int s = 0; s < hp.n_src; ++s) {
+          if (leader)
+            tma_load_4d(dst + static_cast<size_t>(s) * hp.a_part_bytes, &maps.a[s], &fullA[sa], c * 64,
+                        (tw << 3) + hp.dx_min[s], (th << 4) + hp.dy_min[s], n);
+        }
+        __syncwarp();
+        if (++sa == hp.n_a_stages) sa = 0, pa ^= 1;
+        for (int t = 0; t < p.n_taps; ++t) {
+          wait_bounded(&emptyB[sb], pb ^ 1);
+          if (leader) {
+            mbar_expect_tx(&fullB[sb], hp.b_bytes);
+            bulk_load(sB + static_cast<size_t>(sb) * hp.b_bytes,
+                      wbase + static_cast<long long>(p.tap_wrow[t]) * hp.w_tap_stride + c * hp.w_chunk_stride,
+                      hp.b_bytes, &fullB[sb]);
+          }
+          __syncwarp();
+          if (++sb == hp.n_b_stages) sb = 0, pb ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t sbo_a = static_cast<uint32_t>(hp.pitch) * 128u;
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      wait_bounded(&tempty[acc], aphase ^ 1);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+      for (int c = 0; c < hp.n_chunks; ++c) {
+        wait_bounded(&fullA[sa], pa);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(sA + static_cast<size_t>(sa) * hp.a_stage_bytes), 16, sbo_a,
+                                               SWZ_128B);
+        for (int t = 0; t < p.n_taps; ++t) {
+          wait_bounded(&fullB[sb], pb);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + hp.a_tap_off16[t];
+          const uint64_t bdesc = make_smem_desc(smem_u32(sB + static_cast<size_t>(sb) * hp.b_bytes), 16, 1024, SWZ_128B);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (c | t | k) != 0);
+          }
+          if (leader) umma_commit(&emptyB[sb]);
+          __syncwarp();
+          if (++sb == hp.n_b_stages) sb = 0, pb ^= 1;
+        }
+        if (leader) umma_commit(&emptyA[sa]);
+        __syncwarp();
+        if (++sa == hp.n_a_stages) sa = 0, pa ^= 1;
+      }
+      if (leader) umma_commit(&tfull[acc]);
+      __syncwarp();
+      if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
+    }
+  } else {
+    const int group = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int bw = row & 7, bh = row >> 3;
+    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+    int acc = 0, i = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+      if ((i & 1) == group) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        const int tw = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int n = mt / p.tiles_h;
+        const int w = (tw << 3) + bw, h = (th << 4) + bh;
+        const bool valid = (w < p.W) && (h < p.H);
+        const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+        const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
+                                            (w >> p.add_shift) * p.add_sw)
+                                         : 0;
+        wait_bounded(&tfull[acc], aphase);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+        for (int c = 0; c < p.n_tile; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          const int col = nt * p.n_tile + c;
+          if (valid && col < p.Cout) {
+            if (p.phase_cout) {
+              const int ph = col / p.phase_cout;
+              const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
+              epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale);
+            } else {
+              epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Plans the wide-layer halo launch (needs the image-packed weights); false = use the generic kernel.
+static bool plan_halo2(const dfgan_conv_desc* d, Halo2K& hp, int& n_tile, int& smem_bytes) {
+  if (!d->wpack_img || d->Cin % 64 || d->Cin < 128 || d->Cout % 16) return false;
+  if (d->W < 8 || d->H < 16) return false;
+  int dy_max[DFGAN_MAX_SRC], dx_max[DFGAN_MAX_SRC];
+  bool used[DFGAN_MAX_SRC] = {false, false, false, false};
+  for (int s = 0; s < DFGAN_MAX_SRC; ++s) hp.dy_min[s] = hp.dx_min[s] = dy_max[s] = dx_max[s] = 0;
+  for (int t = 0; t < d->n_taps; ++t) {
+    const int s = d->taps[t].src;
+    if (s < 0 || s >= d->n_src) return false;
+    const int dy = d->taps[t].dy, dx = d->taps[t].dx;
+    if (!used[s]) {
+      used[s] = true;
+      hp.dy_min[s] = dy_max[s] = dy;
+      hp.dx_min[s] = dx_max[s] = dx;
+    } else {
+      hp.dy_min[s] = dy < hp.dy_min[s] ? dy : hp.dy_min[s];
+      dy_max[s] = dy > dy_max[s] ? dy : dy_max[s];
+      hp.dx_min[s] = dx < hp.dx_min[s] ? dx : hp.dx_min[s];
+      dx_max[s] = dx > dx_max[s] ? dx : dx_max[s];
+    }
+  }
+  int ext_h = 0, ext_w = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    if (!used[s]) return false;
+    ext_h = dy_max[s] - hp.dy_min[s] > ext_h ? dy_max[s] - hp.dy_min[s] : ext_h;
+    ext_w = dx_max[s] - hp.dx_min[s] > ext_w ? dx_max[s] - hp.dx_min[s] : ext_w;
+  }
+  if (ext_h > 2 || ext_w > 2) return false;
+  n_tile = d->Cout <= 256 ? d->Cout : 256;
+  if (d->Cout % n_tile || n_tile % 8) return false;
+  hp.n_src = d->n_src, hp.n_chunks = d->Cin / 64;
+  hp.pitch = 8 + ext_w, hp.hal_h = 16 + ext_h;
+  hp.a_part_bytes = (static_cast<uint32_t>(hp.hal_h * hp.pitch * 128) + 1023u) & ~1023u;
+  hp.a_stage_bytes = hp.a_part_bytes * static_cast<uint32_t>(d->n_src);
+  hp.b_bytes = static_cast<uint32_t>(n_tile) * 128u;
+  hp.n_acc = n_tile <= 128 ? 4 : 2;
+  const size_t cap = 220 * 1024, fixed = 1024 + 512;
+  // at least 2 halo stages and 3 weight stages; prefer a third halo stage, then as many weight stages as fit
+  if (fixed + 2 * hp.a_stage_bytes + 3 * hp.b_bytes > cap) return false;
+  hp.n_a_stages = (fixed + 3 * hp.a_stage_bytes + 4 * hp.b_bytes <= cap) ? 3 : 2;
+  int nb = static_cast<int>((cap - fixed - hp.n_a_stages * hp.a_stage_bytes) / hp.b_bytes);
+  hp.n_b_stages = nb > 8 ? 8 : nb;
+  smem_bytes = static_cast<int>(fixed + hp.n_a_stages * hp.a_stage_bytes + hp.n_b_stages * hp.b_bytes);
+  for (int t = 0; t < d->n_taps; ++t) {
+    const int s = d->taps[t].src;
+    const uint32_t row0 = static_cast<uint32_t>((d->taps[t].dy - hp.dy_min[s]) * hp.pitch + (d->taps[t].dx - hp.dx_min[s]));
+    hp.a_tap_off16[t] = (static_cast<uint32_t>(s) * hp.a_part_bytes + row0 * 128u) >> 4;
+  }
+  // image layout: [slot][chunk][w_rows_per_slot][64]; a tap's wrow is slot * rows_per_slot (rows, not bytes)
+  hp.w_chunk_stride = static_cast<long long>(d->img_rows_per_slot) * 128;
+  hp.w_tap_stride = static_cast<long long>(hp.n_chunks) * 128;   // per ROW of wrow: slot stride / rows_per_slot
+  hp.wimg = static_cast<const uint8_t*>(d->wpack_img);
+  return true;
+}
+
 static void brick_geometry(int W, int H, int& lbw, int& lbh) {
   int bw = 1;
   while (bw < W && bw < 16) bw <<= 1;
@@ -1144,7 +1398,8 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
       if (grid > cap) grid = cap;
       const double pix = static_cast<double>(d->N) * d->H * d->W;
-      ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, launch_bytes(d), stream);
+      ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
+                        launch_bytes(d), stream);
 #define DFGAN_LAUNCH_HALO(CI, NTAPS)                                                                      \
   do {                                                                                                    \
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, NTAPS>,                                     \
@@ -1166,6 +1421,47 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       else DFGAN_LAUNCH_HALO_C(32);
 #undef DFGAN_LAUNCH_HALO_C
 #undef DFGAN_LAUNCH_HALO
+      count_launch();
+      DFGAN_CUDA_CHECK_LAUNCH();
+      return DFGAN_OK;
+    }
+  }
+
+  {
+    Halo2K h2{};
+    int smem2 = 0, nt2 = 0;
+    static const bool halo2_off = getenv("DFGAN_NO_HALO2") != nullptr;
+    if (!halo2_off && d->n_tile_hint == 0 && plan_halo2(d, h2, nt2, smem2)) {
+      ConvK k{};
+      ConvMaps maps{};
+      k.lbw = 3, k.lbh = 4;
+      k.tiles_w = (d->W + 7) / 8, k.tiles_h = (d->H + 15) / 16, k.tiles_n = d->N;
+      k.n_tile = nt2;
+      k.n_tiles_n = d->Cout / nt2;
+      k.total_tiles = k.tiles_w * k.tiles_h * k.tiles_n * k.n_tiles_n;
+      k.N = d->N, k.H = d->H, k.W = d->W, k.Cout = d->Cout;
+      k.n_taps = d->n_taps, k.n_chunks = h2.n_chunks;
+      for (int t = 0; t < d->n_taps; ++t) {
+        k.tap_src[t] = d->taps[t].src, k.tap_dy[t] = d->taps[t].dy, k.tap_dx[t] = d->taps[t].dx;
+        k.tap_wrow[t] = d->taps[t].wrow;
+      }
+      k.idesc = make_idesc_bf16(128, k.n_tile, 0, 0);
+      fill_epilogue(k, d);
+      for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
+        const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
+        if (v.C != d->Cin) return DFGAN_E_SHAPE;
+        int rc = make_map_nhwc(&maps.a[s], v, 64, h2.pitch, h2.hal_h, 1);
+        if (rc) return rc;
+      }
+      int grid = k.total_tiles;
+      const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
+      if (grid > cap) grid = cap;
+      const double pix = static_cast<double>(d->N) * d->H * d->W;
+      ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
+                        launch_bytes(d), stream);
+      cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      conv_halo2_kernel<<<grid, kHaloThreads, smem2, stream>>>(maps, k, h2);
       count_launch();
       DFGAN_CUDA_CHECK_LAUNCH();
       return DFGAN_OK;
@@ -1230,7 +1526,8 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
   if (grid > cap) grid = cap;
   const double pix = static_cast<double>(d->N) * d->H * d->W;
-  ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin, launch_bytes(d), stream);
+  ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
+                    launch_bytes(d), stream);
   cudaError_t e;
   if (BK == 64) {
     e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

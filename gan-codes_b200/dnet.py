@@ -66,10 +66,13 @@ class DPacked:
         pp.add(params["img_forward.0.weight"], self.w0_d, transpose=True, rows_pad=16)
         for (p, cin, cout, sc), b in zip(self.plan, self.blocks):
             w4, w3 = params[p + ".residual_conv.0.weight"], params[p + ".residual_conv.2.weight"]
-            pp.add(w4, b["w4_f"])
-            pp.add(w4, b["w4_d"], transpose=True, slots=co.s2dgrad_merged_slots() if cin <= MERGE_MAX else None)
-            pp.add(w3, b["w3_f"])
-            pp.add(w3, b["w3_d"], transpose=True)
+            pp.add_with_image(w4, b["w4_f"])
+            if cin <= MERGE_MAX:
+                pp.add_with_image(w4, b["w4_d"], transpose=True, slots=co.s2dgrad_merged_slots(), group=4)
+            else:
+                pp.add_with_image(w4, b["w4_d"], transpose=True)
+            pp.add_with_image(w3, b["w3_f"])
+            pp.add_with_image(w3, b["w3_d"], transpose=True)
             if sc:
                 pp.add(params[p + ".scale_conv.weight"], b["ws_f"], scale=0.25)
                 pp.add(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)

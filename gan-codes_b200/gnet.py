@@ -68,11 +68,12 @@ class GPacked:
         slots = co.subpixel_slots()
         for i, ((p, c1, c2, sc), b) in enumerate(zip(self.plan, self.blocks)):
             w1, w2 = params[p + ".conv_1.weight"], params[p + ".conv_2.weight"]
-            pp.add(w1, b["w1_f"], slots=None if i == 0 else
-                   (co.subpixel_merged_slots() if c2 <= MERGE_MAX else slots))
-            pp.add(w1, b["w1_d"], transpose=True, slots=None if i == 0 else slots)
-            pp.add(w2, b["w2_f"])
-            pp.add(w2, b["w2_d"], transpose=True)
+            merged = i > 0 and c2 <= MERGE_MAX
+            pp.add_with_image(w1, b["w1_f"], slots=None if i == 0 else (co.subpixel_merged_slots() if merged else slots),
+                              group=4 if merged else 1)
+            pp.add_with_image(w1, b["w1_d"], transpose=True, slots=None if i == 0 else slots)
+            pp.add_with_image(w2, b["w2_f"])
+            pp.add_with_image(w2, b["w2_d"], transpose=True)
             if sc:
                 pp.add(params[p + ".scale_conv.weight"], b["ws_f"])
                 pp.add(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)

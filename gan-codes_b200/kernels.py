@@ -162,7 +162,8 @@ class LinearTable:
 
 
 # ------------------------------------------------------------------------------------ packing / optimiser
-def pack_weights(w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False):
+def pack_weights(w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False,
+                 image=False):
     """fp32 OIHW -> bf16 [n_slots*rows_pad, cols_pad].  slots: list of lists of source tap indices (default:
     one slot per tap).  as_matrix: treat [Co, Ci, kh, kw] as [Co, Ci*kh*kw, 1, 1] (stem im2col weights)."""
     assert w.dtype == F32 and w.is_contiguous() and w.is_cuda and out.dtype == BF16 and out.is_contiguous()
@@ -176,9 +177,11 @@ def pack_weights(w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None,
     cols = co if transpose else ci
     rows_pad, cols_pad = rows_pad or rows, cols_pad or cols
     assert out.numel() == len(slots) * rows_pad * cols_pad, (out.shape, len(slots), rows_pad, cols_pad)
+    from . import convops
+    convops.IMAGE_OF.pop(out.data_ptr(), None)   # a re-used address must not inherit a stale image
     flat = (C.c_int8 * (len(slots) * 4))(*[(s[j] if j < len(s) else -1) for s in slots for j in range(4)])
     _call("dfgan_pack_weights", _p(w), _p(out), co, ci, kk, int(transpose), rows_pad, cols_pad, len(slots),
-          C.cast(flat, C.c_void_p), scale, _s())
+          C.cast(flat, C.c_void_p), scale, int(image), _s())
 
 
 class PackPlan:
@@ -187,10 +190,14 @@ class PackPlan:
 
     def __init__(self, device):
         self.device, self.entries, self.blocks, self.dev = device, [], 0, None
+        self.images = []
         self.esize = _lib.lib().dfgan_pack_entry_size()
 
-    def add(self, w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False):
+    def add(self, w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False,
+            image=False):
         assert self.dev is None and w.dtype == F32 and w.is_contiguous() and out.dtype == BF16 and out.is_contiguous()
+        from . import convops
+        convops.IMAGE_OF.pop(out.data_ptr(), None)   # a re-used address must not inherit a stale image
         co, ci, kh, kw = w.shape
         if as_matrix:
             ci, kh, kw = ci * kh * kw, 1, 1
@@ -201,13 +208,28 @@ class PackPlan:
         assert out.numel() == len(slots) * rows_pad * cols_pad
         flat = (C.c_int8 * (len(slots) * 4))(*[(s[j] if j < len(s) else -1) for s in slots for j in range(4)])
         buf = (C.c_uint8 * self.esize)()
+        if image:
+            assert cols_pad % 64 == 0
         nb = _lib.lib().dfgan_pack_entry_fill(C.cast(buf, C.c_void_p), _p(w), _p(out), co, ci, kh * kw,
                                               int(transpose), rows_pad, cols_pad, len(slots),
-                                              C.cast(flat, C.c_void_p), scale, self.blocks)
+                                              C.cast(flat, C.c_void_p), scale, int(image), self.blocks)
         if nb < 0:
             _lib.check(nb, "dfgan_pack_entry_fill")
         self.entries.append(bytes(buf))
         self.blocks += nb
+
+    def add_with_image(self, w, out, *, group=1, **kw):
+        """`add` plus, for wide operands (K = columns a multiple of 64 and >= 128), a second copy in the swizzled
+        shared-memory image layout registered for the wide-layer halo kernel (convops.IMAGE_OF)."""
+        from . import convops
+        self.add(w, out, **kw)
+        cols = out.shape[1]
+        if cols % 64 == 0 and cols >= 128:
+            img = torch.empty_like(out)
+            self.add(w, img, image=group, **kw)
+            n_slots = len(kw["slots"]) if kw.get("slots") is not None else w.shape[2] * w.shape[3]
+            convops.register_image(out, img, (out.shape[0] // n_slots) * group)
+            self.images.append(img)
 
     def run(self):
         if self.dev is None:

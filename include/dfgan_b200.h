@@ -96,6 +96,9 @@ typedef struct dfgan_conv_desc {
   int64_t tab_stride;
   float* out_nchw;
   int32_t co_valid, tanh_out;
+  const void* wpack_img;      /* optional: the same operand packed with image=1 (dfgan_pack_weights); enables the
+                                 wide-layer halo kernel (C_in % 64 == 0, C_in >= 128) */
+  int32_t img_rows_per_slot;  /* rows_pad the image was packed with (rows between consecutive 64-column chunks) */
   int32_t phase_cout; /* > 0: Cout == 4*phase_cout; column block p=(a,c) is written to pixel (2h+a, 2w+c) of the
                          outputs (merged sub-pixel phases), bias / tables / addend are indexed by co % phase_cout */
 } dfgan_conv_desc;
@@ -192,16 +195,18 @@ int dfgan_linear_batched(const dfgan_linear_item* items_dev, int n_items, int B,
                          int mode, dfgan_stream_t st);
 
 /* fp32 OIHW weights -> bf16 GEMM operand [n_slots][rows_pad][cols_pad]; slot s = scale * sum of the source
- * taps slot_taps[s][0..3] (-1 = unused; HOST array); transpose 0: rows=co, cols=ci; 1: rows=ci, cols=co. */
+ * taps slot_taps[s][0..3] (-1 = unused; HOST array); transpose 0: rows=co, cols=ci; 1: rows=ci, cols=co.
+ * image=1 writes the operand as [slot][64-column chunk][rows_pad][64] with every row's 16-byte pieces XOR-swizzled by
+ * (row & 7), i.e. the SWIZZLE_128B shared-memory image, so a weight tile is ONE contiguous bulk copy (wpack_img). */
 int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int transpose, int rows_pad,
-                       int cols_pad, int n_slots, const int8_t* slot_taps, float scale, dfgan_stream_t st);
+                       int cols_pad, int n_slots, const int8_t* slot_taps, float scale, int image, dfgan_stream_t st);
 /* The same for every weight tensor of a network in ONE launch: a host table of dfgan_pack_entry_size()-byte
  * entries is filled with dfgan_pack_entry_fill (returns the entry's block count; block_start = running sum),
  * copied to the device once, and replayed after every optimiser step by dfgan_pack_batched. */
 int dfgan_pack_entry_size(void);
 int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, int Ci, int KK, int transpose,
                           int rows_pad, int cols_pad, int n_slots, const int8_t* slot_taps, float scale,
-                          int block_start);
+                          int image, int block_start);
 int dfgan_pack_batched(const void* entries_dev, int n_entries, int total_blocks, dfgan_stream_t st);
 /* dw[co][ci][3][3] += un-folded sub-pixel weight gradient folded[16][co][ci]. */
 int dfgan_unfold_subpixel_wgrad(const float* folded, float* dw, int Co, int Ci, dfgan_stream_t st);

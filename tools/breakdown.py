@@ -55,6 +55,19 @@ for nm in ("affine2_fwd", "affine2_bwd", "pool", "dres_bwd", "dot", "im2col3", "
            "adam_step", "sqnorm", "rowsq", "unfold_subpixel_wgrad"):
     wrap(K, nm, pw_sig)
 
+_run = K.PackPlan.run
+
+
+def _timed_run(self):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _run(self)
+    e1.record()
+    REC.append(("pack_plan", (f"{len(self.entries)} entries, {self.blocks} blocks", 0.0), e0, e1))
+
+
+K.PackPlan.run = _timed_run
+
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 torch.manual_seed(0)
 G, D = Generator(32, 100).cuda(), Discriminator(32).cuda()

@@ -193,6 +193,65 @@ def subpixel():
     return ok
 
 
+def _pack_img(w, transpose=False, group=1, **kw):
+    """normal pack + the swizzled-image copy, registered for the wide-layer halo kernel"""
+    import torch
+    from gan_codes_b200 import convops as co, kernels as K
+    out = _pack(w, transpose, **kw)
+    img = torch.empty_like(out)
+    K.pack_weights(w.float().contiguous(), img, transpose=transpose, image=group, **kw)
+    slots = kw.get("slots")
+    n_slots = len(slots) if slots else w.shape[2] * w.shape[3]
+    co.register_image(out, img, out.shape[0] // n_slots * group)
+    return out, img
+
+
+@case
+def halo2():
+    """Wide layers (C_in >= 128): halo tile + bulk-copied pre-swizzled weight tiles vs torch and the generic kernel."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co
+    ok = True
+    for (N, C, Kc, H) in [(2, 128, 128, 64), (2, 256, 256, 32), (3, 512, 256, 16), (2, 128, 512, 32), (1, 256, 64, 64)]:
+        x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        w = (torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5)).bfloat16()
+        b = torch.randn(Kc, device="cuda")
+        ref = F.conv2d(x.float(), w.float(), b, padding=1)
+        wp, keep = _pack_img(w)
+        o1 = torch.empty(N, H, H, Kc, device="cuda", dtype=torch.bfloat16)
+        o2 = torch.empty_like(o1)
+        xn = _nhwc(x)
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o1, bias=b)
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o2, bias=b, n_tile=min(Kc, 256))
+        # 4x4 stride 2 over four parity views (2x2 window per view)
+        w4 = (torch.randn(Kc, C, 4, 4, device="cuda") / (4 * C ** 0.5)).bfloat16()
+        r4 = F.leaky_relu(F.conv2d(x.float(), w4.float(), None, stride=2, padding=1), 0.2)
+        w4p, keep4 = _pack_img(w4)
+        o4 = torch.empty(N, H // 2, H // 2, Kc, device="cuda", dtype=torch.bfloat16)
+        if H // 2 >= 16:
+            co.conv_run(co.parity_views(xn), co.taps_4x4s2(Kc), w4p, Kc, o4, lrelu_pre=True)
+        torch.cuda.synchronize()
+        e = [_rel(o1.permute(0, 3, 1, 2), ref), _rel(o1, o2)]
+        if H // 2 >= 16:
+            e.append(_rel(o4.permute(0, 3, 1, 2), r4))
+        print(f"halo2 N{N} C{C} K{Kc} {H}: " + " ".join(f"{v:.3e}" for v in e))
+        ok &= e[0] < 8e-3 and e[1] < 1e-3 and (len(e) < 3 or e[2] < 8e-3)
+    # merged sub-pixel phases with a wide input (C_in 128 -> 4 x 64)
+    N, C, Kc, H = 2, 128, 64, 32
+    x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+    w = torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5)
+    b = torch.randn(Kc, device="cuda")
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2), w, b, padding=1)
+    wm, keepm = _pack_img(w, slots=co.subpixel_merged_slots(), group=4)
+    out = torch.empty(N, 2 * H, 2 * H, Kc, device="cuda", dtype=torch.bfloat16)
+    co.conv_run([_nhwc(x)], co.taps_merged(Kc), wm, 4 * Kc, out, grid=(N, H, H), bias=b, phase_cout=Kc)
+    torch.cuda.synchronize()
+    e = _rel(out.permute(0, 3, 1, 2), ref)
+    print(f"halo2 merged sub-pixel C128->64 @32: {e:.3e}")
+    return ok and e < 8e-3
+
+
 @case
 def merged():
     """Merged-phase launches: upsample->conv3x3 forward and the 4x4/stride-2 data gradient as ONE conv over 9 shifts."""
