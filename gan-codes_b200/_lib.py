@@ -82,6 +82,8 @@ def _declare(l: C.CDLL) -> None:
     l.dfgan_launch_count.restype = C.c_uint64
     l.dfgan_conv_run.argtypes = [C.POINTER(ConvDesc), C.c_void_p]
     l.dfgan_conv_run.restype = C.c_int
+    l.dfgan_conv_uses_image.argtypes = [C.POINTER(ConvDesc)]
+    l.dfgan_conv_uses_image.restype = C.c_int
     l.dfgan_wgrad_run.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
     l.dfgan_wgrad_run.restype = C.c_int
     l.dfgan_profile_enable.argtypes = [C.c_int]

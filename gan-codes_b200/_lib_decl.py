@@ -15,6 +15,8 @@ class LinearItem(C.Structure):
 def declare(l: C.CDLL) -> None:
     l.dfgan_pack_entry_size.argtypes = []
     l.dfgan_pack_entry_size.restype = C.c_int
+    l.dfgan_pack_entry_bs_offset.argtypes = []
+    l.dfgan_pack_entry_bs_offset.restype = C.c_int
     for name, argtypes in _TABLE.items():
         fn = getattr(l, name)   # AttributeError = header and library disagree: fail loudly
         fn.argtypes = argtypes
@@ -46,5 +48,5 @@ _TABLE: dict = {
 }
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
-           "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size",
+           "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size", "dfgan_pack_entry_bs_offset", "dfgan_conv_uses_image",
            *_TABLE.keys()]

@@ -22,6 +22,10 @@ SLOPE = 0.2
 # packed operand (data_ptr) -> (the same operand in the swizzled shared-memory image layout, rows per image slot);
 # registered by the packers for C_in % 64 == 0, C_in >= 128 and picked up by conv_run for the wide-layer halo kernel
 IMAGE_OF: dict = {}
+# data_ptrs of the operand copies conv_run actually consumed while TRACK_USAGE is on (DFGANTrainer turns it on for
+# its first eager iteration and then drops the never-used copies from the per-step re-pack)
+USED: set = set()
+TRACK_USAGE = False
 
 
 def register_image(wpack: torch.Tensor, wimg: torch.Tensor, rows_per_slot: int) -> None:
@@ -147,6 +151,9 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
     img = IMAGE_OF.get(wpack.data_ptr())
     if img is not None:
         d.wpack_img, d.img_rows_per_slot = img[0].data_ptr(), img[1]
+    if TRACK_USAGE:
+        uses_img = img is not None and _lib.lib().dfgan_conv_uses_image(C.byref(d)) == 1
+        USED.add(img[0].data_ptr() if uses_img else wpack.data_ptr())
     _lib.check(_lib.lib().dfgan_conv_run(C.byref(d), _stream()), "dfgan_conv_run")
 
 

@@ -1355,6 +1355,15 @@ static double launch_bytes(const dfgan_conv_desc* d) {
   return bytes;
 }
 
+// 1 when dfgan_conv_run would take the wide-layer halo kernel (reads wpack_img), 0 when it reads wpack.
+extern "C" int dfgan_conv_uses_image(const dfgan_conv_desc* d) {
+  if (!d) return 0;
+  Halo2K h2{};
+  int smem2 = 0, nt2 = 0;
+  if (getenv("DFGAN_NO_HALO2") != nullptr || d->n_tile_hint != 0) return 0;
+  return plan_halo2(d, h2, nt2, smem2) ? 1 : 0;
+}
+
 extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!d || !d->wpack) return DFGAN_E_ARG;

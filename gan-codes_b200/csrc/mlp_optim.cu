@@ -8,6 +8,8 @@
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
+#include <cstddef>
+
 namespace dfgan {
 
 constexpr int kLinThreads = 256;
@@ -297,6 +299,7 @@ int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int tr
 }
 
 int dfgan_pack_entry_size(void) { return static_cast<int>(sizeof(PackEntry)); }
+int dfgan_pack_entry_bs_offset(void) { return static_cast<int>(offsetof(PackEntry, block_start)); }
 
 /* Fills one host-side table entry (entry_out points at dfgan_pack_entry_size() bytes); returns the number of
  * 256-thread blocks the entry needs, or a negative error.  block_start is the running block offset. */

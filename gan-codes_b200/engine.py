@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
+from . import convops as co
 from . import dnet, gnet
 from . import kernels as K
 
@@ -242,8 +243,18 @@ class DFGANTrainer:
         for dst, src in zip(self._in, (images, sentence_embeds, noise)):
             dst.copy_(src, non_blocking=True)
         if not self.use_graph or self._eager_calls < 2:
+            first = self._eager_calls == 0
             self._eager_calls += 1
+            if first:
+                # learn which copy (tensor-map layout / shared-memory image) of every weight operand this shape
+                # configuration consumes, then stop re-packing the other one after each optimiser step
+                co.USED.clear()
+                co.TRACK_USAGE = True
             self.last = self._run_eager(*self._in)
+            if first:
+                co.TRACK_USAGE = False
+                self.dpk._pp.prune(co.USED)
+                self.gpk._pp.prune(co.USED)
             return self.last
         if self._graph is None:
             self._capture()

@@ -190,12 +190,13 @@ class PackPlan:
 
     def __init__(self, device):
         self.device, self.entries, self.blocks, self.dev = device, [], 0, None
-        self.images = []
+        self.images, self.outs, self.nblocks = [], [], []
+        self.bs_off = _lib.lib().dfgan_pack_entry_bs_offset()
         self.esize = _lib.lib().dfgan_pack_entry_size()
 
     def add(self, w, out, *, transpose=False, rows_pad=0, cols_pad=0, slots=None, scale=1.0, as_matrix=False,
             image=False):
-        assert self.dev is None and w.dtype == F32 and w.is_contiguous() and out.dtype == BF16 and out.is_contiguous()
+        assert w.dtype == F32 and w.is_contiguous() and out.dtype == BF16 and out.is_contiguous()
         from . import convops
         convops.IMAGE_OF.pop(out.data_ptr(), None)   # a re-used address must not inherit a stale image
         co, ci, kh, kw = w.shape
@@ -216,7 +217,29 @@ class PackPlan:
         if nb < 0:
             _lib.check(nb, "dfgan_pack_entry_fill")
         self.entries.append(bytes(buf))
+        self.outs.append(out.data_ptr())
+        self.nblocks.append(nb)
         self.blocks += nb
+
+    def prune(self, used: set) -> int:
+        """Drop the entries whose output operand is not in `used` (data_ptrs); returns how many were dropped.
+        block_start of the kept entries is rewritten in place (last 4 bytes of an entry)."""
+        import struct
+        keep = [i for i, o in enumerate(self.outs) if o in used]
+        dropped = len(self.outs) - len(keep)
+        if dropped == 0 or not keep:
+            return 0
+        entries, start = [], 0
+        for i in keep:
+            e = bytearray(self.entries[i])
+            e[self.bs_off:self.bs_off + 4] = struct.pack("<i", start)
+            entries.append(bytes(e))
+            start += self.nblocks[i]
+        self.entries = entries
+        self.outs = [self.outs[i] for i in keep]
+        self.nblocks = [self.nblocks[i] for i in keep]
+        self.blocks, self.dev = start, None
+        return dropped
 
     def add_with_image(self, w, out, *, group=1, **kw):
         """`add` plus, for wide operands (K = columns a multiple of 64 and >= 128), a second copy in the swizzled

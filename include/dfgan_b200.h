@@ -104,6 +104,9 @@ typedef struct dfgan_conv_desc {
 } dfgan_conv_desc;
 
 int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream);
+/* 1 when dfgan_conv_run(d) reads d->wpack_img (wide-layer halo kernel), 0 when it reads d->wpack: lets a caller
+ * that re-packs weights every optimiser step skip the operand copy it never uses. */
+int dfgan_conv_uses_image(const dfgan_conv_desc* d);
 
 /*
  * dfgan_wgrad_run -- weight gradient of the same tap-list convolution (split-K over pixels, fp32 atomics):
@@ -204,6 +207,7 @@ int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int tr
  * entries is filled with dfgan_pack_entry_fill (returns the entry's block count; block_start = running sum),
  * copied to the device once, and replayed after every optimiser step by dfgan_pack_batched. */
 int dfgan_pack_entry_size(void);
+int dfgan_pack_entry_bs_offset(void); /* byte offset of the int32 block_start inside an entry (host-side re-linking) */
 int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, int Ci, int KK, int transpose,
                           int rows_pad, int cols_pad, int n_slots, const int8_t* slot_taps, float scale,
                           int image, int block_start);
