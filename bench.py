@@ -163,9 +163,29 @@ def run_ours(args):
     def step_dev():
         trainer.step(images_d, sent_d, noise_d)
 
+    # end-to-end step: pinned host inputs in, the three losses out to pinned host memory EVERY step.  The
+    # device->host copy is asynchronous and the host waits for it one call later (double-buffered), so the host
+    # keeps one iteration queued ahead and the next H2D overlaps the running iteration; the last step's losses
+    # are awaited inside the timed region by `drain_e2e`.
+    loss_h = [torch.zeros(3).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "read": 0}
+
     def step_e2e():
+        i = e2e_state["i"]
         out = trainer.step(images_h, sent_h, noise_h)
-        return torch.stack([out["d_loss"], out["gp_loss"], out["g_loss"]]).cpu()
+        if i >= 1:
+            loss_ev[(i - 1) & 1].synchronize()           # losses of the previous step are now on the host
+            e2e_state["read"] += 1
+        loss_h[i & 1].copy_(torch.stack([out["d_loss"], out["gp_loss"], out["g_loss"]]), non_blocking=True)
+        loss_ev[i & 1].record()
+        e2e_state["i"] = i + 1
+
+    def drain_e2e():
+        i = e2e_state["i"]
+        if i >= 1:
+            loss_ev[(i - 1) & 1].synchronize()
+            e2e_state["read"] += 1
 
     # eager pass first (also the graph warm-up): counts OUR kernel launches per step and times every launch of
     # the two GEMM engines with CUDA events on the launching stream (roofline leg)
@@ -187,7 +207,15 @@ def run_ours(args):
     ms = timed(step_dev, args.steps)
     clocks = sampler.summary() if sampler else None
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    drain_e2e()
+    e2e_state.update(i=0, read=0)
+
+    def e2e_region():
+        step_e2e()
+        if e2e_state["i"] == args.steps:
+            drain_e2e()
+    ms_e2e = timed(e2e_region, args.steps)
+    assert e2e_state["read"] == args.steps, e2e_state
     losses = {k: float(v) for k, v in trainer.last.items()}
 
     if rank == 0:

@@ -237,11 +237,29 @@ class DFGANTrainer:
         if images.shape[0] != self.batch:
             raise RuntimeError(f"DFGANTrainer was built for batch {self.batch}, got {images.shape[0]}")
         if self._in is None:
-            self._in = (torch.empty(images.shape, device=dev, dtype=F32),
-                        torch.empty(sentence_embeds.shape, device=dev, dtype=F32),
-                        torch.empty(noise.shape, device=dev, dtype=F32))
-        for dst, src in zip(self._in, (images, sentence_embeds, noise)):
-            dst.copy_(src, non_blocking=True)
+            mk = lambda t: torch.empty(t.shape, device=dev, dtype=F32)  # noqa: E731
+            self._in = (mk(images), mk(sentence_embeds), mk(noise))
+            self._stage = (mk(images), mk(sentence_embeds), mk(noise))
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._ev_h2d, self._ev_free = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_free.record()
+        srcs = (images, sentence_embeds, noise)
+        if all(not t.is_cuda for t in srcs):
+            # host inputs: the H2D copy goes to a staging buffer on a side stream, so it overlaps the previous
+            # iteration still running on the main stream; a device-to-device copy then fills the static inputs
+            main = torch.cuda.current_stream()
+            self._copy_stream.wait_event(self._ev_free)          # previous staging -> static copy has finished
+            with torch.cuda.stream(self._copy_stream):
+                for dst, src in zip(self._stage, srcs):
+                    dst.copy_(src, non_blocking=True)
+                self._ev_h2d.record()
+            main.wait_event(self._ev_h2d)
+            for dst, src in zip(self._in, self._stage):
+                dst.copy_(src, non_blocking=True)
+            self._ev_free.record()
+        else:
+            for dst, src in zip(self._in, srcs):
+                dst.copy_(src, non_blocking=True)
         if not self.use_graph or self._eager_calls < 2:
             first = self._eager_calls == 0
             self._eager_calls += 1
