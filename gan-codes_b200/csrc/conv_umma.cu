@@ -55,6 +55,8 @@ struct ConvK {
   float* out_nchw;  // fp32 [N][co_valid][H][W] store (image boundary), optional tanh
   int co_valid, tanh_out;
   int phase_cout;   // > 0: columns are 4 output phases x phase_cout channels of a 2x-upsampled output grid
+  int col_split;    // halo kernels: both epilogue warpgroups work on EVERY tile (alternate 16-column chunks)
+                    // instead of alternating tiles -- for launches with only 1-2 tiles per CTA
 };
 
 __device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], p.col_split ? 8 : 4);
     }
     mbar_init(bfull, 1);
     fence_mbar_init();
@@ -704,7 +706,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     int acc = 0, i = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-      if ((i & 1) == group) {
+      if (p.col_split || (i & 1) == group) {
         const int tw = tile % p.tiles_w;
         const int r = tile / p.tiles_w;
         const int th = r % p.tiles_h;
@@ -719,7 +721,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-        for (int c = 0; c < p.n_tile; c += 16) {
+        for (int c = p.col_split ? group * 16 : 0; c < p.n_tile; c += p.col_split ? 32 : 16) {
           float v[16];
           tmem_ld16(taddr + c, v);
           if (valid) {
@@ -1110,7 +1112,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       mbar_init(&fullA[i], 1);
       mbar_init(&emptyA[i], 1);
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], p.col_split ? 8 : 4);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&fullB[i], 1);
@@ -1206,7 +1208,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     int acc = 0, i = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-      if ((i & 1) == group) {
+      if (p.col_split || (i & 1) == group) {
         const int nt = tile % p.n_tiles_n;
         int mt = tile / p.n_tiles_n;
         const int tw = mt % p.tiles_w;
@@ -1223,7 +1225,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-        for (int c = 0; c < p.n_tile; c += 16) {
+        for (int c = p.col_split ? group * 16 : 0; c < p.n_tile; c += p.col_split ? 32 : 16) {
           float v[16];
           tmem_ld16(taddr + c, v);
           const int col = nt * p.n_tile + c;
@@ -1406,6 +1408,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       int grid = k.total_tiles;
       const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
       if (grid > cap) grid = cap;
+      k.col_split = (k.total_tiles <= 3 * grid && k.n_tile >= 32) ? 1 : 0;
       const double pix = static_cast<double>(d->N) * d->H * d->W;
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
                         launch_bytes(d), stream);
@@ -1465,6 +1468,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       int grid = k.total_tiles;
       const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
       if (grid > cap) grid = cap;
+      k.col_split = (k.total_tiles <= 3 * grid) ? 1 : 0;
       const double pix = static_cast<double>(d->N) * d->H * d->W;
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
                         launch_bytes(d), stream);
