@@ -192,12 +192,15 @@ def run_ours(args):
     for _ in range(2):
         step_dev()
     trainer.use_graph, graph_wanted = False, trainer.use_graph
+    from gan_codes_b200 import convops as _co
+    side_wanted, _co.SIDE_ENABLED = _co.SIDE_ENABLED, False   # serial launches: per-kernel durations stay clean
     _lib.profile_enable(True)
     l0 = _lib.launch_count()
     ms_eager = timed(step_dev, args.steps)
     launches = _lib.launch_count() - l0
     prof = _lib.profile_read()
     _lib.profile_enable(False)
+    _co.SIDE_ENABLED = side_wanted
     trainer.use_graph = graph_wanted
     for _ in range(max(3, args.warmup)):      # first call captures the CUDA graph, the rest replay it
         step_dev()

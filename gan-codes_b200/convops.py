@@ -28,6 +28,69 @@ USED: set = set()
 TRACK_USAGE = False
 
 
+# ------------------------------------------------------------------------------------ side streams
+# Launches that are independent of the chain on the current stream (weight gradients next to the data-gradient
+# chain, the four sub-pixel phases of one convolution) are issued on side streams: forked from / joined into the
+# current stream with events, so under stream capture they become parallel branches of the CUDA graph and fill the
+# SMs a small-grid kernel leaves idle.  SIDE_ENABLED = False serialises everything on the current stream (used by
+# the per-kernel timing pass of bench.py and by DFGAN_NO_SIDE=1).
+import os as _os
+
+SIDE_ENABLED = _os.environ.get("DFGAN_NO_SIDE", "0") != "1"
+N_SIDE = 3            # streams per pool
+POOL_PHASE, POOL_WGRAD = 0, 1
+_SIDE_STREAMS: dict = {}
+_SIDE_DIRTY: dict = {}
+
+
+def _dev_key(dev) -> int:
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _side_streams(dev) -> list:
+    key = _dev_key(dev)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [[torch.cuda.Stream(device=dev) for _ in range(N_SIDE)] for _ in range(2)]
+        _SIDE_DIRTY[key] = [[False] * N_SIDE for _ in range(2)]
+    return _SIDE_STREAMS[key]
+
+
+class side:
+    """``with side(i, dev, pool):`` -- the body's launches go to side stream i of the pool, ordered after everything
+    issued so far on the current stream.  The body must not allocate; every tensor it touches must stay alive
+    until ``join`` of that pool."""
+
+    def __init__(self, idx: int, dev, pool: int = POOL_WGRAD):
+        self.idx, self.dev, self.pool, self.ctx = idx % N_SIDE, dev, pool, None
+
+    def __enter__(self):
+        if not SIDE_ENABLED:
+            return self
+        s = _side_streams(self.dev)[self.pool][self.idx]
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        _SIDE_DIRTY[_dev_key(self.dev)][self.pool][self.idx] = True
+        self.ctx = torch.cuda.stream(s)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def join(dev, pool: int = POOL_WGRAD) -> None:
+    """The current stream waits for every side stream of the pool that received work since its last join."""
+    key = _dev_key(dev)
+    if not SIDE_ENABLED or key not in _SIDE_STREAMS:
+        return
+    cur = torch.cuda.current_stream(dev)
+    for i, s in enumerate(_SIDE_STREAMS[key][pool]):
+        if _SIDE_DIRTY[key][pool][i]:
+            cur.wait_stream(s)
+            _SIDE_DIRTY[key][pool][i] = False
+
+
 def register_image(wpack: torch.Tensor, wimg: torch.Tensor, rows_per_slot: int) -> None:
     IMAGE_OF[wpack.data_ptr()] = (wimg, rows_per_slot)
 

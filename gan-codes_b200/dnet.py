@@ -144,7 +144,8 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
     n = ctx["n"]
     e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
     g_y = g_emb
-    kept = []
+    kept = []     # also keeps every tensor a side stream reads alive until the join below
+    n_side = 0
     for (p, cin, cout, sc), b, (x, c1, r) in zip(reversed(pk.plan), reversed(pk.blocks), reversed(ctx["saved"])):
         h, w = c1.shape[1], c1.shape[2]
         g_c2 = e(n, h, w, cout)
@@ -164,31 +165,42 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
             co.conv_run([g_c1], co.taps_merged(cin), b["w4_d"], 4 * cin, g_x, grid=(n, h, w), addend=g_s,
                         add_scale=0.25, phase_cout=cin)
         else:
-            for a in (0, 1):
-                for c in (0, 1):
-                    co.conv_run([g_c1], co.taps_4x4s2_dgrad(cin, a, c), b["w4_d"], cin, g_x[:, a::2, c::2, :],
+            # the four input phases are independent launches: phases 1..3 on side streams (parallel graph branches)
+            views = [g_x[:, a::2, c::2, :] for a in (0, 1) for c in (0, 1)]
+            for ph in (1, 2, 3):
+                with co.side(ph - 1, dev, co.POOL_PHASE):
+                    co.conv_run([g_c1], co.taps_4x4s2_dgrad(cin, ph >> 1, ph & 1), b["w4_d"], cin, views[ph],
                                 addend=g_s, add_scale=0.25)
+            co.conv_run([g_c1], co.taps_4x4s2_dgrad(cin, 0, 0), b["w4_d"], cin, views[0], addend=g_s,
+                        add_scale=0.25)
+            co.join(dev, co.POOL_PHASE)
         if grads is not None:
+            # weight gradients leave the data-gradient chain: side stream, joined at the end of the sweep
             w3, w4 = params[p + ".residual_conv.2.weight"], params[p + ".residual_conv.0.weight"]
-            co.wgrad_run([c1], TAPS3_ID, g_c2, grads[p + ".residual_conv.2.weight"], _oihw_strides(w3))
             pv = co.parity_views(x)
-            co.wgrad_run(pv, TAPS4_ID, g_c1, grads[p + ".residual_conv.0.weight"], _oihw_strides(w4))
-            if sc:
-                ws = params[p + ".scale_conv.weight"]
-                co.wgrad_run(pv, TAPS_POOL, g_y, grads[p + ".scale_conv.weight"], _oihw_strides(ws),
-                             scale_imm=0.25)
-        kept.append((g_y, g_c2, g_c1))
+            with co.side(n_side, dev):
+                co.wgrad_run([c1], TAPS3_ID, g_c2, grads[p + ".residual_conv.2.weight"], _oihw_strides(w3))
+            with co.side(n_side + 1, dev):
+                co.wgrad_run(pv, TAPS4_ID, g_c1, grads[p + ".residual_conv.0.weight"], _oihw_strides(w4))
+                if sc:
+                    ws = params[p + ".scale_conv.weight"]
+                    co.wgrad_run(pv, TAPS_POOL, g_y, grads[p + ".scale_conv.weight"], _oihw_strides(ws),
+                                 scale_imm=0.25)
+            n_side += 2
+        kept.append((g_y, g_c2, g_c1, g_s))
         g_y = g_x
     if grads is not None:
-        co.wgrad_run([ctx["xcol"]], [(0, 0, 0, 0)], g_y, grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
+        with co.side(n_side, dev):
+            co.wgrad_run([ctx["xcol"]], [(0, 0, 0, 0)], g_y, grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
         K.pool(g_y, None, shift=0, colsum=grads["img_forward.0.bias"])
     if cots is not None:
-        cots.update(blocks=list(reversed(kept)), x0=g_y)
-    if not need_gx:
-        return None
-    hh = g_y.shape[1]
-    gx = torch.empty(n, 3, hh, hh, device=dev, dtype=F32)
-    co.conv_run([g_y], co.taps_3x3_dgrad(16), pk.w0_d, 16, None, out_nchw=gx, co_valid=3)
+        cots.update(blocks=[k[:3] for k in reversed(kept)], x0=g_y)
+    gx = None
+    if need_gx:
+        hh = g_y.shape[1]
+        gx = torch.empty(n, 3, hh, hh, device=dev, dtype=F32)
+        co.conv_run([g_y], co.taps_3x3_dgrad(16), pk.w0_d, 16, None, out_nchw=gx, co_valid=3)
+    co.join(dev)
     return gx
 
 
@@ -206,7 +218,10 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
     K.im2col3(t_img, tcol, rowscale=rowscale)
     t_x = e(n, h, w, pk.n_c)
     co.conv_run([tcol], co.taps_1x1(), pk.w0_f, pk.n_c, t_x)
-    co.wgrad_run([tcol], [(0, 0, 0, 0)], cots["x0"], grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
+    # every weight gradient only consumes the tangent chain: side streams, joined at the end of the sweep
+    with co.side(0, dev):
+        co.wgrad_run([tcol], [(0, 0, 0, 0)], cots["x0"], grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
+    keep, n_side = [tcol], 1
     for (p, cin, cout, sc), b, (x, c1, r), (c_y, c_c2, c_c1) in zip(pk.plan, pk.blocks, ctx["saved"],
                                                                   cots["blocks"]):
         h, w = h // 2, w // 2
@@ -214,21 +229,27 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
         t_s = e(n, h, w, cout)
         if sc:
             co.conv_run(pv, TAPS_POOL, b["ws_f"], cout, t_s)
-            co.wgrad_run(pv, TAPS_POOL, c_y, grads[p + ".scale_conv.weight"],
-                         _oihw_strides(params[p + ".scale_conv.weight"]), scale_imm=0.25)
         else:
             K.pool(t_x, t_s, shift=1, scale=0.25)
+        with co.side(n_side, dev):
+            if sc:
+                co.wgrad_run(pv, TAPS_POOL, c_y, grads[p + ".scale_conv.weight"],
+                             _oihw_strides(params[p + ".scale_conv.weight"]), scale_imm=0.25)
+            co.wgrad_run(pv, TAPS4_ID, c_c1, grads[p + ".residual_conv.0.weight"],
+                         _oihw_strides(params[p + ".residual_conv.0.weight"]))
         t_c1 = e(n, h, w, cout)
         co.conv_run(pv, co.taps_4x4s2(cout), b["w4_f"], cout, t_c1, mask_src=c1)
-        co.wgrad_run(pv, TAPS4_ID, c_c1, grads[p + ".residual_conv.0.weight"],
-                     _oihw_strides(params[p + ".residual_conv.0.weight"]))
+        with co.side(n_side + 1, dev):
+            co.wgrad_run([t_c1], TAPS3_ID, c_c2, grads[p + ".residual_conv.2.weight"],
+                         _oihw_strides(params[p + ".residual_conv.2.weight"]))
         t_y, t_r = e(n, h, w, cout), e(n, h, w, cout)
         co.conv_run([t_c1], co.taps_3x3(cout), b["w3_f"], cout, t_y, mask_src=r, aux=t_r,
                     scale_dev=params[p + ".gamma"], addend=t_s)
-        co.wgrad_run([t_c1], TAPS3_ID, c_c2, grads[p + ".residual_conv.2.weight"],
-                     _oihw_strides(params[p + ".residual_conv.2.weight"]))
         K.dot(c_y, t_r, grads[p + ".gamma"])
+        keep += [t_x, t_c1]
+        n_side += 2
         t_x = t_y
+    co.join(dev)
     return t_x
 
 

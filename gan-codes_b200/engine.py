@@ -96,6 +96,7 @@ class DFGANTrainer:
             self.dpk = dnet.DPacked(self.ds.params)
             self.mlp = gnet.GMlp(self.gs.params, self.gpk.plan, batch, self.gs.grads)
         dev = self.gs.flat.device
+        co._side_streams(dev)      # created here, never inside a stream capture
         self.ones = torch.ones(batch, device=dev, dtype=F32)
         self.last: Dict[str, torch.Tensor] = {}
         # The iteration is ~400 kernel launches; replaying it as ONE CUDA graph removes the host launch cost

@@ -207,11 +207,17 @@ def generator_forward(pk: GPacked, params, mlp: GMlp, noise: torch.Tensor, sent:
                         bias=params[p + ".conv_1.bias"], aux=h1, out2=a34, post_mode=2, tables=t34,
                         tab_stride=mlp.T, phase_cout=c2)
         elif up:
-            for a in (0, 1):
-                for c in (0, 1):
-                    co.conv_run([a12], co.taps_subpixel_fwd(c2, a, c), b["w1_f"], c2, None, grid=(n, h, h),
-                                bias=params[p + ".conv_1.bias"], aux=h1[:, a::2, c::2, :],
-                                out2=a34[:, a::2, c::2, :], post_mode=2, tables=t34, tab_stride=mlp.T)
+            # four independent phase launches: phases 1..3 on side streams (parallel branches of the CUDA graph)
+            def phase(ph):
+                a, c = ph >> 1, ph & 1
+                co.conv_run([a12], co.taps_subpixel_fwd(c2, a, c), b["w1_f"], c2, None, grid=(n, h, h),
+                            bias=params[p + ".conv_1.bias"], aux=h1[:, a::2, c::2, :],
+                            out2=a34[:, a::2, c::2, :], post_mode=2, tables=t34, tab_stride=mlp.T)
+            for ph in (1, 2, 3):
+                with co.side(ph - 1, dev, co.POOL_PHASE):
+                    phase(ph)
+            phase(0)
+            co.join(dev, co.POOL_PHASE)
         else:
             co.conv_run([a12], co.taps_3x3(c2), b["w1_f"], c2, None, bias=params[p + ".conv_1.bias"], aux=h1,
                         out2=a34, post_mode=2, tables=t34, tab_stride=mlp.T)
@@ -243,8 +249,12 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
     dbo = torch.zeros(3, device=dev, dtype=F32)
     K.tanh_bwd_pack(g_img.contiguous(), img, g_t, dbias=dbo)
     grads["conv_out.1.bias"].add_(dbo)
-    co.wgrad_run([act], TAPS3_ID, g_t, grads["conv_out.1.weight"], _oihw_strides(params["conv_out.1.weight"]),
-                 co_valid=3)
+    # weight gradients leave the data-gradient chain: side streams, joined before the MLP backward; `keep` holds
+    # every tensor they read until then
+    keep, n_side = [g_t], 1
+    with co.side(0, dev):
+        co.wgrad_run([act], TAPS3_ID, g_t, grads["conv_out.1.weight"], _oihw_strides(params["conv_out.1.weight"]),
+                     co_valid=3)
     g_z = e(*z.shape)
     co.conv_run([g_t], co.taps_3x3_dgrad(pk.c_last), pk.wo_d, pk.c_last, g_z, mask_src=z)
     mlp.d_tab.zero_()
@@ -257,8 +267,9 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
         # conv_2: data gradient (unscaled; gamma is applied inside the affine backward) and weight gradient
         q = e(n, hh, hh, c2)
         co.conv_run([g_z], co.taps_3x3_dgrad(c2), b["w2_d"], c2, q)
-        co.wgrad_run([a34], TAPS3_ID, g_z, grads[p + ".conv_2.weight"], _oihw_strides(params[p + ".conv_2.weight"]),
-                     scale_dev=gamma)
+        with co.side(n_side, dev):
+            co.wgrad_run([a34], TAPS3_ID, g_z, grads[p + ".conv_2.weight"],
+                         _oihw_strides(params[p + ".conv_2.weight"]), scale_dev=gamma)
         # shortcut branch: 2x2 sum (backward of the nearest upsample) + per-channel sums of g_z
         cs = torch.zeros(c2, device=dev, dtype=F32)
         pooled = e(n, h, h, c2) if up else None
@@ -274,25 +285,32 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
         g_a12 = e(n, h, h, c1)
         w1 = params[p + ".conv_1.weight"]
         if up:
-            co.conv_run(_phases(g_h1), co.taps_subpixel_dgrad(c1), b["w1_d"], c1, g_a12)
             folded = torch.zeros(16, c2, c1, device=dev, dtype=F32)
-            for a in (0, 1):
-                for c in (0, 1):
-                    co.wgrad_run([a12], co.taps_subpixel_wgrad(a, c), g_h1[:, a::2, c::2, :], folded,
-                                 (c1, 1, c2 * c1))
-            K.unfold_subpixel_wgrad(folded, grads[p + ".conv_1.weight"])
+            co.conv_run(_phases(g_h1), co.taps_subpixel_dgrad(c1), b["w1_d"], c1, g_a12)
+            with co.side(n_side + 1, dev):
+                for a in (0, 1):
+                    for c in (0, 1):
+                        co.wgrad_run([a12], co.taps_subpixel_wgrad(a, c), g_h1[:, a::2, c::2, :], folded,
+                                     (c1, 1, c2 * c1))
+                K.unfold_subpixel_wgrad(folded, grads[p + ".conv_1.weight"])
+            keep.append(folded)
         else:
             co.conv_run([g_h1], co.taps_3x3_dgrad(c1), b["w1_d"], c1, g_a12)
-            co.wgrad_run([a12], TAPS3_ID, g_h1, grads[p + ".conv_1.weight"], _oihw_strides(w1))
+            with co.side(n_side + 1, dev):
+                co.wgrad_run([a12], TAPS3_ID, g_h1, grads[p + ".conv_1.weight"], _oihw_strides(w1))
         if sc:
             grads[p + ".scale_conv.bias"].add_(cs)
             t = e(n, h, h, c1)
             co.conv_run([pooled], co.taps_1x1(), b["ws_d"], c1, t)
-            co.wgrad_run([z_prev], [(0, 0, 0, 0)], pooled, grads[p + ".scale_conv.weight"], (c1, 1, 0))
+            with co.side(n_side + 2, dev):
+                co.wgrad_run([z_prev], [(0, 0, 0, 0)], pooled, grads[p + ".scale_conv.weight"], (c1, 1, 0))
         else:
             t = pooled
         g_prev = e(n, h, h, c1)
         K.affine2_bwd(g_a12, z_prev, g_prev, mlp.tables(p, 1), mlp.tables(p, 1, mlp.d_tab), mlp.T, g_add=t)
+        keep += [g_z, g_h1, pooled]
+        n_side += 3
         g_z = g_prev
+    co.join(dev)
     K.nhwc_to_nchw(g_z, mlp.g_x0f.view(n, pk.c0, 4, 4))
     mlp.backward()
