@@ -214,6 +214,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on its results are needed.  The successor may start its own prologue right away.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int BW = 1 << p.lbw, BH = 1 << p.lbh;
   const int k_iters = p.n_taps * p.n_chunks;
@@ -403,6 +407,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on its results are needed.  The successor may start its own prologue right away.
+  pdl_wait();
+  pdl_launch_dependents();
   const int blocks_per_tile = 128 >> p.lcb;
 
   if (warp == 0) {
@@ -609,6 +617,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on its results are needed.  The successor may start its own prologue right away.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool leader = elect_one();
@@ -881,6 +893,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on its results are needed.  The successor may start its own prologue right away.
+  pdl_wait();
+  pdl_launch_dependents();
 
   // contiguous slice of pixel bricks for this CTA
   const int t0 = static_cast<int>((static_cast<long long>(p.pix_tiles) * blockIdx.x) / gridDim.x);
@@ -1128,6 +1144,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel; from here on its results are needed.  The successor may start its own prologue right away.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     const bool leader = elect_one();
@@ -1417,7 +1437,8 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, NTAPS>,                                     \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
-    conv_halo_kernel<CI, NTAPS><<<grid, kHaloThreads, smem_halo, stream>>>(maps, k, hp);                  \
+    e = launch_pdl(conv_halo_kernel<CI, NTAPS>, grid, kHaloThreads, smem_halo, stream, maps, k, hp);      \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                     \
   } while (0)
 #define DFGAN_LAUNCH_HALO_C(CI)                                                                           \
   do {                                                                                                    \
@@ -1474,7 +1495,8 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
                         launch_bytes(d), stream);
       cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
       if (e != cudaSuccess) return static_cast<int>(e);
-      conv_halo2_kernel<<<grid, kHaloThreads, smem2, stream>>>(maps, k, h2);
+      e = launch_pdl(conv_halo2_kernel, grid, kHaloThreads, smem2, stream, maps, k, h2);
+      if (e != cudaSuccess) return static_cast<int>(e);
       count_launch();
       DFGAN_CUDA_CHECK_LAUNCH();
       return DFGAN_OK;
@@ -1546,12 +1568,14 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    conv_umma_kernel<64><<<grid, kConvThreads, smem, stream>>>(maps, k);
+    e = launch_pdl(conv_umma_kernel<64>, grid, kConvThreads, smem, stream, maps, k);
+    if (e != cudaSuccess) return static_cast<int>(e);
   } else {
     e = cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    conv_umma_kernel<32><<<grid, kConvThreads, smem, stream>>>(maps, k);
+    e = launch_pdl(conv_umma_kernel<32>, grid, kConvThreads, smem, stream, maps, k);
+    if (e != cudaSuccess) return static_cast<int>(e);
   }
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
@@ -1599,7 +1623,8 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
     cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<CI, CO>,                                       \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
-    wgrad_halo_kernel<CI, CO><<<grid, kConvThreads, smem_halo, stream>>>(maps, hk);                       \
+    e = launch_pdl(wgrad_halo_kernel<CI, CO>, grid, kConvThreads, smem_halo, stream, maps, hk);           \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                     \
   } while (0)
       if (d->Cin == 32 && d->Cout == 32) DFGAN_LAUNCH_WHALO(32, 32);
       else if (d->Cin == 32 && d->Cout == 64) DFGAN_LAUNCH_WHALO(32, 64);
@@ -1693,7 +1718,8 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  wgrad_umma_kernel<<<grid, kConvThreads, smem, stream>>>(maps, k);
+  e = launch_pdl(wgrad_umma_kernel, grid, kConvThreads, smem, stream, maps, k);
+  if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;

@@ -1,5 +1,6 @@
 #include "host_common.h"
 
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -19,6 +20,11 @@ encode_tiled_fn get_encode_tiled() {
       fn = reinterpret_cast<encode_tiled_fn>(p);
   });
   return fn;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("DFGAN_NO_PDL") == nullptr;
+  return on;
 }
 
 int num_sms() {

@@ -40,6 +40,20 @@ int make_map_halo(CUtensorMap* m, const dfgan_view4& v, int bw, int bh);
 // bf16 row-major matrix [rows][cols] -> 2-D tiled tensor map with box {bc, brows}.
 int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int bc, int brows);
 
+// Launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait() before it touches
+// global memory).  DFGAN_NO_PDL=1 falls back to plain stream-ordered launches.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

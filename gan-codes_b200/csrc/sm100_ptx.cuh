@@ -180,6 +180,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become
+// resident while its predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and
+// its memory is visible, pdl_launch_dependents() lets the successor's CTAs start their prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

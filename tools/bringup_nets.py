@@ -308,6 +308,47 @@ def engine():
 
 
 @case
+def graph_side_consistency():
+    """The CUDA-graph replay with side-stream branches and programmatic dependent launches must compute what
+    the serial eager launches compute.  Three iterations bring the trainer to its captured state; the optimiser
+    state is snapshotted, iteration 4 runs as a graph replay, the snapshot is restored and the same iteration runs
+    again as serial eager launches: gradient buffers, losses and updated parameters agree up to atomic-order
+    noise (Adam is sign-like at beta1 = 0, so runs from different states cannot be compared)."""
+    torch, O, g_sd, d_sd, images, sent, noise = _states(batch=4, ws=1.0)
+    from gan_codes_b200 import convops as co
+    from gan_codes_b200.engine import DFGANTrainer
+    G, D = _ref_modules(torch, O, g_sd, d_sd)
+    tr = DFGANTrainer(G, D, 4, use_graph=True)
+    for _ in range(3):
+        tr.step(images, sent, noise)
+    torch.cuda.synchronize()
+    assert tr._graph is not None
+    bufs = [t for st in (tr.gs, tr.ds) for t in (st.flat, st.m, st.v, st.step_count)]
+    snap = [t.clone() for t in bufs]
+
+    def run():
+        out = tr.step(images, sent, noise)
+        torch.cuda.synchronize()
+        return dict(dg=tr.ds.grad.clone(), gg=tr.gs.grad.clone(), dp=tr.ds.flat.clone(), gp=tr.gs.flat.clone(),
+                    losses=[out[k].item() for k in ("d_loss", "gp_loss", "g_loss")])
+    a = run()
+    for t, s0 in zip(bufs, snap):
+        t.copy_(s0)
+    tr.dpk.refresh(tr.ds.params)
+    tr.gpk.refresh(tr.gs.params)
+    side_was, co.SIDE_ENABLED, tr.use_graph = co.SIDE_ENABLED, False, False
+    try:
+        b = run()
+    finally:
+        co.SIDE_ENABLED, tr.use_graph = side_was, True
+    print("  losses graph+side", a["losses"], "| eager serial", b["losses"])
+    rows = [("D gradient buffer (GP phase)", rel(a["dg"], b["dg"])), ("G gradient buffer", rel(a["gg"], b["gg"])),
+            ("D parameters", rel(a["dp"], b["dp"])), ("G parameters", rel(a["gp"], b["gp"]))]
+    rows += [(f"loss {i}", abs(x - y) / (abs(y) + 1e-6)) for i, (x, y) in enumerate(zip(a["losses"], b["losses"]))]
+    return _report(rows, 2e-2)
+
+
+@case
 def gp_identity_full():
     """Size-independent property at the benchmark batch (B = 32, 256x256): the tangent sweep in direction
     v = coef * (gx, gs) must return tangent logits coef_b * (|gx_b|^2 + |gs_b|^2) -- ties the first-order dgrad
