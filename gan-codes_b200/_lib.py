@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libdfgan_b200.so")
+LIB_PATH = os.environ.get("DFGAN_LIB") or os.path.join(_HERE, "_C", "libdfgan_b200.so")   # DFGAN_LIB: A/B builds
 
 MAX_SRC = 4
 MAX_TAPS = 16

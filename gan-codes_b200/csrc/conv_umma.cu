@@ -57,6 +57,8 @@ struct ConvK {
   int phase_cout;   // > 0: columns are 4 output phases x phase_cout channels of a 2x-upsampled output grid
   int col_split;    // halo kernels: both epilogue warpgroups work on EVERY tile (alternate 16-column chunks)
                     // instead of alternating tiles -- for launches with only 1-2 tiles per CTA
+  int dbg;          // DFGAN_DBG bit mask (conv_halo_kernel only): 1 skip epilogue body, 2 skip MMAs, 4 skip TMA loads,
+                    // 8 skip tcgen05.ld -- bottleneck isolation, results are garbage
 };
 
 __device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -551,6 +553,27 @@ constexpr size_t kSmemBudget = 200 * 1024;
 // up to four TMEM accumulator stages.
 constexpr int kHaloThreads = 320;
 
+// Tap geometries whose A-descriptor offsets are compile-time constants (taps sorted by source, dy, dx).  The MMA
+// issue loop is bound by moving descriptor words from vector to uniform registers (R2UR, ~20 cycles each, 11 per tap
+// when the offsets are runtime values added in the vector datapath); with immediates the whole tile is one R2UR'd base
+// plus UIADD3.64 per MMA.  GEOM_RUNTIME keeps host-computed offsets (any tap list).
+enum : int { GEOM_RUNTIME = 0, GEOM_1 = 1, GEOM_3X3 = 2, GEOM_2X2X4 = 3, GEOM_POOL4 = 4, GEOM_2X2 = 5 };
+__host__ __device__ constexpr int geom_taps(int geom) {
+  return geom == GEOM_1 ? 1 : (geom == GEOM_3X3 ? 9 : (geom == GEOM_2X2X4 ? 16 : (geom == GEOM_RUNTIME ? 0 : 4)));
+}
+// (halo-tile part + start row of tap t) >> 4 for channel count cin
+__host__ __device__ constexpr uint32_t geom_off16(int geom, int cin, int t) {
+  const uint32_t row = static_cast<uint32_t>(cin) * 2u;
+  if (geom == GEOM_3X3) return (static_cast<uint32_t>((t / 3) * 10 + (t % 3)) * row) >> 4;
+  if (geom == GEOM_2X2) return (static_cast<uint32_t>((t / 2) * 9 + (t % 2)) * row) >> 4;
+  if (geom == GEOM_POOL4) return (static_cast<uint32_t>(t) * 16u * 8u * row) >> 4;
+  if (geom == GEOM_2X2X4) {
+    const uint32_t part = (17u * 9u * row + 1023u) & ~1023u;
+    return (static_cast<uint32_t>(t / 4) * part + static_cast<uint32_t>(((t % 4) / 2) * 9 + (t % 2)) * row) >> 4;
+  }
+  return 0;
+}
+
 struct HaloK {
   int dy_min[DFGAN_MAX_SRC], dx_min[DFGAN_MAX_SRC];
   int n_parts[DFGAN_MAX_SRC];  // halo tiles per source (mode 0: one per dx)
@@ -569,7 +592,7 @@ __device__ __forceinline__ uint64_t with_base_offset(uint64_t desc, uint32_t sad
   return desc | (static_cast<uint64_t>((saddr >> 7) & 7u) << 49);
 }
 
-template <int CIN, int NT>
+template <int CIN, int GEOM>
 __global__ void __launch_bounds__(kHaloThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p,
                      const __grid_constant__ HaloK hp) {
@@ -637,6 +660,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       const int th = r % p.tiles_h;
       const int n = r / p.tiles_h;
       wait_bounded(&empty[stage], phase ^ 1);
+      if (p.dbg & 4) {
+        if (leader) mbar_arrive(&full[stage]);
+        __syncwarp();
+        if (++stage == kAStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        continue;
+      }
       if (leader) mbar_expect_tx(&full[stage], tx);
       uint8_t* dst = sA + static_cast<size_t>(stage) * a_stage_bytes;
       for (int s = 0; s < hp.n_src; ++s)
@@ -675,23 +707,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       // tools/ubench/mma_cost.cu): tap offsets come precomputed from the host, the tap loop is unrolled at
       // compile time (NT) so they are constant-bank immediates.
       const uint64_t adesc0 = make_smem_desc(a_base, 16, sbo_a, swz);
-      if (NT > 0) {
+      if (leader && !(p.dbg & 2)) {
+        // ONE elected-lane region for the whole tile; the two bases pass through an empty asm so that nothing
+        // derived from them is hoisted out of the tile loop into vector registers (each use would cost two R2UR)
+        uint64_t ad0 = adesc0, bd0 = bdesc0;
+        asm volatile("" : "+l"(ad0), "+l"(bd0));
+        constexpr int NT = geom_taps(GEOM);
+        if (NT > 0) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const uint64_t adesc = adesc0 + hp.a_tap_off16[t];
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(t) * b_step16;
+          for (int t = 0; t < NT; ++t) {
+            const uint64_t adesc = ad0 + geom_off16(GEOM, CIN, t);
+            const uint64_t bdesc = bd0 + static_cast<uint64_t>(t) * b_step16;
 #pragma unroll
-          for (int k = 0; k < CIN / 16; ++k) {
-            if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+            for (int k = 0; k < CIN / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
           }
-        }
-      } else {
-        for (int t = 0; t < p.n_taps; ++t) {
-          const uint64_t adesc = adesc0 + hp.a_tap_off16[t];
-          const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(t) * b_step16;
+        } else {
+          for (int t = 0; t < p.n_taps; ++t) {
+            const uint64_t adesc = ad0 + hp.a_tap_off16[t];
+            const uint64_t bdesc = bd0 + static_cast<uint64_t>(t) * b_step16;
 #pragma unroll
-          for (int k = 0; k < CIN / 16; ++k) {
-            if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+            for (int k = 0; k < CIN / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
           }
         }
       }
@@ -735,8 +770,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
         for (int c = p.col_split ? group * 16 : 0; c < p.n_tile; c += p.col_split ? 32 : 16) {
           float v[16];
+          if (p.dbg & 8) continue;
           tmem_ld16(taddr + c, v);
-          if (valid) {
+          if (valid && !(p.dbg & 1)) {
             if (p.phase_cout) {
               const int ph = c / p.phase_cout;
               const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
@@ -937,20 +973,24 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       tc_fence_after();
       const uint32_t st_base = smem_u32(smem + static_cast<size_t>(ps.stage) * p.stage_bytes);
       const uint32_t g_base = st_base + static_cast<uint32_t>(p.n_src) * p.a_part_bytes;
-      // a handful of uniform instructions per MMA: group offsets are host-precomputed, both loops unrolled
+      // ONE elected-lane region per brick; the bases pass through an empty asm so nothing derived from them is
+      // hoisted into vector registers (see conv_halo_kernel): the issue loop is UIADD3.64 + UTCHMMA only
       const uint64_t adesc0 = make_smem_desc(st_base, kRowA, sbo_a, swz_a);
       const uint64_t bdesc0 = make_smem_desc(g_base, kRowG, sbo_g, swz_g);
       const uint32_t acc_flag = tile > t0;
+      if (leader) {
+        uint64_t ad0 = adesc0, bd0 = bdesc0, ks = a_kstep16;
+        asm volatile("" : "+l"(ad0), "+l"(bd0), "+l"(ks));
 #pragma unroll
-      for (int g = 0; g < kWHaloGroupsMax; ++g) {
-        if (g < p.n_groups) {
-          const uint64_t ag = adesc0 + p.grp_off16[g];
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * COUT);
+        for (int g = 0; g < kWHaloGroupsMax; ++g) {
+          if (g < p.n_groups) {
+            uint64_t ag = ad0 + p.grp_off16[g];
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(g * COUT);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA: image rows 2k and 2k+1 of the brick
-            if (leader)
-              umma_bf16(d_tmem, ag + static_cast<uint64_t>(k) * a_kstep16, bdesc0 + static_cast<uint64_t>(k) * g_kstep16,
-                        p.idesc, acc_flag | (k != 0));
+            for (int k = 0; k < 8; ++k) {   // 16 pixels per MMA: image rows 2k and 2k+1 of the brick
+              umma_bf16(d_tmem, ag, bd0 + static_cast<uint64_t>(k) * g_kstep16, p.idesc, acc_flag | (k != 0));
+              ag += ks;                     // running add: one uniform add per MMA instead of hoisted multiples
+            }
           }
         }
       }
@@ -1402,7 +1442,20 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     HaloK hp{};
     int smem_halo = 0;
     static const bool halo_off = getenv("DFGAN_NO_HALO") != nullptr;
-    if (!halo_off && d->n_tile_hint == 0 && plan_halo(d, hp, smem_halo)) {
+    // taps sorted by (source, dy, dx): the sum does not depend on the order, and the standard geometries then have
+    // compile-time descriptor offsets (geom_off16)
+    dfgan_conv_desc ds = *d;
+    for (int i = 1; i < ds.n_taps && i < DFGAN_MAX_TAPS; ++i)
+      for (int j = i; j > 0; --j) {
+        const dfgan_tap &a = ds.taps[j - 1], &b = ds.taps[j];
+        const bool gt = a.src != b.src ? a.src > b.src : (a.dy != b.dy ? a.dy > b.dy : a.dx > b.dx);
+        if (!gt) break;
+        const dfgan_tap tmp = ds.taps[j - 1];
+        ds.taps[j - 1] = ds.taps[j];
+        ds.taps[j] = tmp;
+      }
+    if (!halo_off && d->n_tile_hint == 0 && plan_halo(&ds, hp, smem_halo)) {
+      d = &ds;
       ConvK k{};
       ConvMaps maps{};
       k.lbw = 3, k.lbh = 4;
@@ -1429,25 +1482,39 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
       if (grid > cap) grid = cap;
       k.col_split = (k.total_tiles <= 3 * grid && k.n_tile >= 32) ? 1 : 0;
+      k.dbg = getenv("DFGAN_DBG") ? atoi(getenv("DFGAN_DBG")) : 0;
+      // standard geometry?  (host-computed offsets must equal the compile-time table)
+      int geom = GEOM_RUNTIME;
+      static const bool geom_off = getenv("DFGAN_NO_GEOM") != nullptr;
+      for (int g = GEOM_1; g <= GEOM_2X2 && !geom_off; ++g) {
+        if (geom_taps(g) != d->n_taps) continue;
+        bool same = true;
+        for (int t = 0; t < d->n_taps; ++t) same = same && hp.a_tap_off16[t] == geom_off16(g, d->Cin, t);
+        if (same) {
+          geom = g;
+          break;
+        }
+      }
       const double pix = static_cast<double>(d->N) * d->H * d->W;
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
                         launch_bytes(d), stream);
-#define DFGAN_LAUNCH_HALO(CI, NTAPS)                                                                      \
+#define DFGAN_LAUNCH_HALO(CI, GEOM)                                                                       \
   do {                                                                                                    \
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, NTAPS>,                                     \
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, GEOM>,                                      \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
-    e = launch_pdl(conv_halo_kernel<CI, NTAPS>, grid, kHaloThreads, smem_halo, stream, maps, k, hp);      \
+    e = launch_pdl(conv_halo_kernel<CI, GEOM>, grid, kHaloThreads, smem_halo, stream, maps, k, hp);       \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
   } while (0)
 #define DFGAN_LAUNCH_HALO_C(CI)                                                                           \
   do {                                                                                                    \
-    switch (d->n_taps) {                                                                                  \
-      case 1: DFGAN_LAUNCH_HALO(CI, 1); break;                                                            \
-      case 4: DFGAN_LAUNCH_HALO(CI, 4); break;                                                            \
-      case 9: DFGAN_LAUNCH_HALO(CI, 9); break;                                                            \
-      case 16: DFGAN_LAUNCH_HALO(CI, 16); break;                                                          \
-      default: DFGAN_LAUNCH_HALO(CI, 0); break;                                                           \
+    switch (geom) {                                                                                       \
+      case GEOM_1: DFGAN_LAUNCH_HALO(CI, GEOM_1); break;                                                  \
+      case GEOM_3X3: DFGAN_LAUNCH_HALO(CI, GEOM_3X3); break;                                              \
+      case GEOM_2X2X4: DFGAN_LAUNCH_HALO(CI, GEOM_2X2X4); break;                                          \
+      case GEOM_POOL4: DFGAN_LAUNCH_HALO(CI, GEOM_POOL4); break;                                          \
+      case GEOM_2X2: DFGAN_LAUNCH_HALO(CI, GEOM_2X2); break;                                              \
+      default: DFGAN_LAUNCH_HALO(CI, GEOM_RUNTIME); break;                                                \
     }                                                                                                     \
   } while (0)
       if (d->Cin == 64) DFGAN_LAUNCH_HALO_C(64);
