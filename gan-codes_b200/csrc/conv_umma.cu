@@ -79,6 +79,21 @@ struct PipeState {
   }
 };
 
+// pack 16 floats to bf16 (round-to-nearest-even), store them, and replace v by the stored (rounded) values:
+// bf16 -> fp32 is a 16-bit shift / mask of the packed word, no second conversion
+__device__ __forceinline__ void store_round_bf16x16(__nv_bfloat16* dst, float* v) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  d[0] = make_uint4(u[0], u[1], u[2], u[3]);
+  d[1] = make_uint4(u[4], u[5], u[6], u[7]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[2 * i] = __uint_as_float(u[i] << 16);
+    v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v) {
   uint4 s0, s1;
   s0.x = pack_bf16x2(v[0], v[1]), s0.y = pack_bf16x2(v[2], v[3]);
@@ -131,9 +146,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
     if (p.aux) {
       // continue from the stored (bf16) value: what the backward pass reads back is exactly what
       // the rest of the forward used
-      store_bf16x16(p.aux + o_off + col, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+      store_round_bf16x16(p.aux + o_off + col, v);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] *= scale;
@@ -153,12 +166,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
         if (col + i < p.co_valid) dst[(col + i) * hw] = p.tanh_out ? tanhf(v[i]) : v[i];
       }
     }
-    if (p.out) store_bf16x16(p.out + o_off + col, v);
+    if (p.out) {
+      if (p.post_mode) store_round_bf16x16(p.out + o_off + col, v);
+      else store_bf16x16(p.out + o_off + col, v);
+    }
     if (p.post_mode) {
       // the follow-up pointwise chain is evaluated on the bf16-rounded value that `out`/`aux`
       // hold, so a backward pass that recomputes it from the stored tensor sees identical masks
+      if (!p.out) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
+      }
       if (p.post_mode == 2) {
         const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
         float ga[16], ba[16];
