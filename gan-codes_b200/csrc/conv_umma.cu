@@ -125,8 +125,43 @@ __device__ __forceinline__ float round_bf16(float x) {
 }
 
 // One 16-column chunk of the fused epilogue for one output pixel (see dfgan_conv_run in the header).
+// mask / addend rows of a chunk, requested ahead of use (their DRAM latency was the largest marginal cost of the
+// fused epilogues, tools/prof_epilogue.py): chunk 0 before the accumulator-ready wait, chunk c+1 before chunk c
+struct EpiPre {
+  uint4 m0, m1, a0, a1;
+};
+__device__ __forceinline__ void epi_prefetch(const ConvK& p, EpiPre& e, bool on, long long m_off, long long a_off) {
+  if (!on) return;
+  if (p.mask_src) {
+    const uint4* sp = reinterpret_cast<const uint4*>(p.mask_src + m_off);
+    e.m0 = __ldg(sp), e.m1 = __ldg(sp + 1);
+  }
+  if (p.addend) {
+    const uint4* sp = reinterpret_cast<const uint4*>(p.addend + a_off);
+    e.a0 = __ldg(sp), e.a1 = __ldg(sp + 1);
+  }
+}
+// request the mask / addend rows of the chunk at tile column c (output column gcol) for this thread's pixel
+__device__ __forceinline__ void epi_pre_issue(const ConvK& p, EpiPre& e, bool valid, int gcol, int c, int n, int h,
+                                              int w, long long o_off, long long a_off) {
+  if (!(p.mask_src || p.addend) || !valid || c >= p.n_tile || gcol >= p.Cout) return;
+  int col = gcol;
+  long long oo = o_off;
+  if (p.phase_cout) {
+    const int ph = gcol / p.phase_cout;
+    col = gcol - ph * p.phase_cout;
+    oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
+  }
+  epi_prefetch(p, e, true, oo + col, a_off + col);
+}
+__device__ __forceinline__ void unpack_bf16x16(const uint4& s0, const uint4& s1, float* v) {
+  const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) unpack_bf16x2(u[i], v[2 * i], v[2 * i + 1]);
+}
+
 __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], int col, int n, int h, int w,
-                                               long long o_off, long long a_off, float scale) {
+                                               long long o_off, long long a_off, float scale, const EpiPre& pre) {
     if (p.bias) {
       float b[16];
       load_f32x16(p.bias + col, b);
@@ -139,7 +174,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
     }
     if (p.mask_src) {
       float m[16];
-      load_bf16x16(p.mask_src + o_off + col, m);
+      unpack_bf16x16(pre.m0, pre.m1, m);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : p.slope);
     }
@@ -152,7 +187,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
     for (int i = 0; i < 16; ++i) v[i] *= scale;
     if (p.addend) {
       float a[16];
-      load_bf16x16(p.addend + a_off + col, a);
+      unpack_bf16x16(pre.a0, pre.a1, a);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += p.add_scale * a[i];
     }
@@ -326,21 +361,25 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
                                           (w >> p.add_shift) * p.add_sw)
                                        : 0;
+      EpiPre nxt{};
+      epi_pre_issue(p, nxt, valid, nt * p.n_tile, 0, n, h, w, o_off, a_off);
       wait_bounded(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
       for (int c = 0; c < p.n_tile; c += 16) {
+        const EpiPre cur = nxt;
+        const int col = nt * p.n_tile + c;
+        epi_pre_issue(p, nxt, valid, col + 16, c + 16, n, h, w, o_off, a_off);
         float v[16];
         tmem_ld16(taddr + c, v);
-        const int col = nt * p.n_tile + c;
         if (valid && col < p.Cout) {
           if (p.phase_cout) {
             const int ph = col / p.phase_cout;
             const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-            epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale);
+            epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale, cur);
           } else {
-            epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale);
+            epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale, cur);
           }
         }
       }
@@ -782,11 +821,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
                                             (w >> p.add_shift) * p.add_sw)
                                          : 0;
+        const int c0 = p.col_split ? group * 16 : 0, cstep = p.col_split ? 32 : 16;
+        EpiPre nxt{};
+        epi_pre_issue(p, nxt, valid, c0, c0, n, h, w, o_off, a_off);
         wait_bounded(&tfull[acc], aphase);
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-        for (int c = p.col_split ? group * 16 : 0; c < p.n_tile; c += p.col_split ? 32 : 16) {
+        for (int c = c0; c < p.n_tile; c += cstep) {
+          const EpiPre cur = nxt;
+          epi_pre_issue(p, nxt, valid, c + cstep, c + cstep, n, h, w, o_off, a_off);
           float v[16];
           if (p.dbg & 8) continue;
           tmem_ld16(taddr + c, v);
@@ -794,9 +838,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
             if (p.phase_cout) {
               const int ph = c / p.phase_cout;
               const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-              epilogue_chunk(p, v, c - ph * p.phase_cout, n, h, w, oo, a_off, scale);
+              epilogue_chunk(p, v, c - ph * p.phase_cout, n, h, w, oo, a_off, scale, cur);
             } else {
-              epilogue_chunk(p, v, c, n, h, w, o_off, a_off, scale);
+              epilogue_chunk(p, v, c, n, h, w, o_off, a_off, scale, cur);
             }
           }
         }
@@ -1299,21 +1343,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
                                             (w >> p.add_shift) * p.add_sw)
                                          : 0;
+        const int c0 = p.col_split ? group * 16 : 0, cstep = p.col_split ? 32 : 16;
+        EpiPre nxt{};
+        epi_pre_issue(p, nxt, valid, nt * p.n_tile + c0, c0, n, h, w, o_off, a_off);
         wait_bounded(&tfull[acc], aphase);
         tc_fence_after();
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-        for (int c = p.col_split ? group * 16 : 0; c < p.n_tile; c += p.col_split ? 32 : 16) {
+        for (int c = c0; c < p.n_tile; c += cstep) {
+          const EpiPre cur = nxt;
+          const int col = nt * p.n_tile + c;
+          epi_pre_issue(p, nxt, valid, col + cstep, c + cstep, n, h, w, o_off, a_off);
           float v[16];
           tmem_ld16(taddr + c, v);
-          const int col = nt * p.n_tile + c;
           if (valid && col < p.Cout) {
             if (p.phase_cout) {
               const int ph = col / p.phase_cout;
               const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-              epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale);
+              epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale, cur);
             } else {
-              epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale);
+              epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale, cur);
             }
           }
         }
