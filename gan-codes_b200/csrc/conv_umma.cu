@@ -1290,37 +1290,39 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t sbo_a = static_cast<uint32_t>(hp.pitch) * 128u;
-    int sa = 0, sb = 0, acc = 0;
-    uint32_t pa = 0, pb = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      wait_bounded(&tempty[acc], aphase ^ 1);
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-      for (int c = 0; c < hp.n_chunks; ++c) {
-        wait_bounded(&fullA[sa], pa);
-        const uint64_t adesc0 = make_smem_desc(smem_u32(sA + static_cast<size_t>(sa) * hp.a_stage_bytes), 16, sbo_a,
-                                               SWZ_128B);
-        for (int t = 0; t < p.n_taps; ++t) {
-          wait_bounded(&fullB[sb], pb);
-          tc_fence_after();
-          const uint64_t adesc = adesc0 + hp.a_tap_off16[t];
-          const uint64_t bdesc = make_smem_desc(smem_u32(sB + static_cast<size_t>(sb) * hp.b_bytes), 16, 1024, SWZ_128B);
+    // The whole issue loop runs in the ONE elected lane (waits included): no per-tap warp synchronisation, and
+    // every descriptor derives from per-stage bases with uniform adds (see conv_halo_kernel)
+    if (leader) {
+      const uint32_t sbo_a = static_cast<uint32_t>(hp.pitch) * 128u;
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        wait_bounded(&tempty[acc], aphase ^ 1);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        for (int c = 0; c < hp.n_chunks; ++c) {
+          wait_bounded(&fullA[sa], pa);
+          uint64_t ad0 = make_smem_desc(sA_u + static_cast<uint32_t>(sa) * hp.a_stage_bytes, 16, sbo_a, SWZ_128B);
+          asm volatile("" : "+l"(ad0));
+          for (int t = 0; t < p.n_taps; ++t) {
+            wait_bounded(&fullB[sb], pb);
+            tc_fence_after();
+            const uint64_t adesc = ad0 + hp.a_tap_off16[t];
+            uint64_t bdesc = make_smem_desc(sB_u + static_cast<uint32_t>(sb) * hp.b_bytes, 16, 1024, SWZ_128B);
+            asm volatile("" : "+l"(bdesc));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (c | t | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (c | t | k) != 0);
+            umma_commit(&emptyB[sb]);
+            if (++sb == hp.n_b_stages) sb = 0, pb ^= 1;
           }
-          if (leader) umma_commit(&emptyB[sb]);
-          __syncwarp();
-          if (++sb == hp.n_b_stages) sb = 0, pb ^= 1;
+          umma_commit(&emptyA[sa]);
+          if (++sa == hp.n_a_stages) sa = 0, pa ^= 1;
         }
-        if (leader) umma_commit(&emptyA[sa]);
-        __syncwarp();
-        if (++sa == hp.n_a_stages) sa = 0, pa ^= 1;
+        umma_commit(&tfull[acc]);
+        if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
       }
-      if (leader) umma_commit(&tfull[acc]);
-      __syncwarp();
-      if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
     }
+    __syncwarp();
   } else {
     const int group = (warp - 2) >> 2;
     const int q = warp & 3;
