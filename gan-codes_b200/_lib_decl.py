@@ -45,6 +45,9 @@ _TABLE: dict = {
     "dfgan_unfold_subpixel_wgrad": [P, P, I, I, P],
     "dfgan_sqnorm": [P, L, P, P],
     "dfgan_adam_step": [P, P, P, P, L, P, P, F, F, F, F, F, F, P],
+    "dfgan_conv2d_f32_fprop": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "dfgan_conv2d_f32_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "dfgan_conv2d_f32_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
 }
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",

@@ -13,6 +13,10 @@ Autograd contract: outputs carry grad_fn, `.backward()` fills every parameter's 
 MA-GP double backward (deep_fusion_gan/model.py:59-85, 202-210), implemented as a tangent-forward sweep
 (SURVEY App. C-3).  Parameters are fp32 in the reference layout; compute is bf16 tensor-core with fp32
 accumulation.  CUDA only: calling a module whose parameters are not on a CUDA device raises.
+
+Precision tiers: the default "bf16" is the fast path above.  `module.set_precision("fp32")` runs the same module
+graph on the CUDA-core fp32 convolution kernels (gan_codes_b200.fp32), which agree with the reference's fp32
+(TF32-off) path to 1e-4 -- the verification tier of north_star.
 """
 from __future__ import annotations
 
@@ -22,7 +26,7 @@ from typing import Dict, List
 import torch
 import torch.nn as nn
 
-from . import dnet, gnet
+from . import dnet, fp32, gnet
 from . import kernels as K
 
 F32 = torch.float32
@@ -37,6 +41,17 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 def _as_f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(F32).contiguous()
+
+
+class _PrecisionMixin:
+    _precision = "bf16"
+
+    def set_precision(self, precision: str):
+        """"bf16" (tensor-core fast path, default) or "fp32" (CUDA-core verification tier, gan_codes_b200.fp32)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self._precision = precision
+        return self
 
 
 class _FlatGrads:
@@ -136,7 +151,7 @@ class _GeneratorFn(torch.autograd.Function):
         return (None, None, None, *[fg.views[n] for n in module._names])
 
 
-class Generator(nn.Module):
+class Generator(_PrecisionMixin, nn.Module):
     """generator/model.py:8-47."""
 
     def __init__(self, n_channels: int, latent_dim: int):
@@ -165,6 +180,8 @@ class Generator(nn.Module):
     def forward(self, noise_vector: torch.Tensor, sentence_embed: torch.Tensor) -> torch.Tensor:
         tensors = [p for _, p in self.named_parameters()]
         _require_cuda(tensors[0], "Generator.forward")
+        if self._precision == "fp32":
+            return fp32.generator_forward(self, noise_vector, sentence_embed)
         return _GeneratorFn.apply(self, noise_vector, sentence_embed, *tensors)
 
 
@@ -297,7 +314,7 @@ class _LogitsBwdFn(torch.autograd.Function):
         return (None, None, None, None, t_logit.view(-1, 1, 1, 1), fg.views[names[0]], fg.views[names[1]])
 
 
-class Discriminator(nn.Module):
+class Discriminator(_PrecisionMixin, nn.Module):
     """discriminator/model.py:8-59."""
 
     def __init__(self, n_c: int, sentence_embed_dim: int = 256):
@@ -328,11 +345,15 @@ class Discriminator(nn.Module):
     def build_embeds(self, image: torch.Tensor) -> torch.Tensor:
         tensors = [p for n, p in self.named_parameters() if n.startswith("img_forward.")]
         _require_cuda(tensors[0], "Discriminator.build_embeds")
+        if self._precision == "fp32":
+            return fp32.build_embeds(self, image)
         return _EmbedsFn.apply(self, image, *tensors)
 
     def get_logits(self, image_embed: torch.Tensor, sentence_embed: torch.Tensor) -> torch.Tensor:
         w0, w2 = self.img_sentence_forward[0].weight, self.img_sentence_forward[2].weight
         _require_cuda(w0, "Discriminator.get_logits")
+        if self._precision == "fp32":
+            return fp32.get_logits(self, image_embed, sentence_embed)
         return _LogitsFn.apply(self, image_embed, sentence_embed, w0, w2)
 
     def forward(self, image, sentence_embed):   # convenience; the reference trainer never calls it

@@ -222,6 +222,23 @@ int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, con
                     const int* step, float gscale, float max_norm, float lr, float b1, float b2, float eps,
                     dfgan_stream_t st);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * fp32 precision tier (north_star: "1e-4 for fp32 / tf32-off"): plain CUDA-core convolution on the reference's own
+ * layouts -- x [N,Cin,H,W], w [Cout,Cin,KH,KW], y [N,Cout,OH,OW], all fp32 contiguous, stride 1 or 2, KH*KW <= 16.
+ * Replaces nn.Conv2d / nn.Linear (as 1x1 on a 1x1 grid) of generator/residual_block.py:16,21,25,
+ * generator/model.py:13,28, generator/fusion_block.py:8-18, discriminator/residual_block.py:11,13,19,
+ * discriminator/model.py:13,31,33 and their autograd (aten::convolution_backward, _convolution_double_backward):
+ * the three operators are closed under differentiation.  Verification tier, not the fast path. */
+int dfgan_conv2d_f32_fprop(const float* x, const float* w, const float* bias /* may be NULL */, float* y, int N,
+                           int Cin, int H, int W, int Cout, int KH, int KW, int stride, int pad, int OH, int OW,
+                           dfgan_stream_t st);
+/* gx[N,Cin,H,W] = d/dx <gy, conv(x, w)> */
+int dfgan_conv2d_f32_dgrad(const float* gy, const float* w, float* gx, int N, int Cin, int H, int W, int Cout, int KH,
+                           int KW, int stride, int pad, int OH, int OW, dfgan_stream_t st);
+/* gw[Cout,Cin,KH,KW] = d/dw <gy, conv(x, w)>  (overwrites gw; deterministic reduction order) */
+int dfgan_conv2d_f32_wgrad(const float* x, const float* gy, float* gw, int N, int Cin, int H, int W, int Cout, int KH,
+                           int KW, int stride, int pad, int OH, int OW, dfgan_stream_t st);
+
 /* Per-launch timing of the two GEMM engines with CUDA events on the launching stream (bench.py roofline leg).
  * dfgan_profile_read: out[e*4 + {0: summed ms, 1: executed FLOPs, 2: algorithmic bytes, 3: launches}], e = 0 for
  * dfgan_conv_run, 1 for dfgan_wgrad_run; synchronises the device and clears the records. */

