@@ -228,6 +228,11 @@ def run_ours(args):
         dom = max(("conv", "wgrad"), key=lambda k: prof[k]["ms"])
         p = prof[dom]
         ach = p["flops"] / (p["ms"] / 1e3) / 1e12 if p["ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+        if dom == "conv" and B == 32 and os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = round(json.load(fh)["dram_bytes_per_launch"], 1)
         line = {
             "metric": "train images/sec (G+D step, 256x256)", "value": round(value, 2), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -248,7 +253,11 @@ def run_ours(args):
             "roofline": {"kernel": "conv_umma_kernel (dfgan_conv_run)" if dom == "conv" else
                          "wgrad_umma_kernel (dfgan_wgrad_run)",
                          "bound": "tensor", "achieved": round(ach, 2), "peak": tf_sust, "unit": "TFLOP/s",
-                         "frac": round(ach / tf_sust, 4), "traffic": None,
+                         "frac": round(ach / tf_sust, 4), "traffic": traffic,
+                         "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu, "
+                                         "cold cache), averaged over the conv-engine launches of one iteration; "
+                                         "see profiles/r01_traffic.json",
+                         "algorithmic_bytes_per_launch": round(p["bytes"] / max(p["launches"], 1), 1),
                          "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": int(p["launches"]), "kernel_ms_per_step": round(p["ms"] / args.steps, 3),
                          "share_of_step": round(p["ms"] / ms, 4),
