@@ -137,33 +137,76 @@ __device__ __forceinline__ long long pack_dst(const PackP& p, int slot, int row,
   const int nc = p.cols_pad >> 6, c = col >> 6, j = (col & 63) >> 3, e = col & 7;
   return ((static_cast<long long>(slot_i) * nc + c) * rows_i + row_i) * 64 + (((j ^ (row_i & 7)) << 3) + e);
 }
-// One thread per (row, col) of the operand: it reads the kh*kw taps of its (co, ci) pair ONCE (36-64 contiguous
-// bytes) and writes every slot's value; consecutive threads = consecutive columns, so all stores are coalesced.
-// (A first version used one thread per OUTPUT element: 4-byte reads at a 36-byte stride, repeated per slot --
-// 1.4 ms for the discriminator's operands against ~0.1 ms of memory traffic.)
-__device__ __forceinline__ void pack_body(const PackP& p, long long i, float* sm) {
+// One 256-thread block per 32 x 32 tile of (co, ci) pairs.  Phase 1 stages the tile's fp32 weights (32 runs of
+// 32*KK contiguous floats) in shared memory with fully coalesced loads; phase 2 writes every slot of the operand with
+// 16-byte stores (8 consecutive columns per thread), reading the tile transposed when the operand is.  (History: one
+// thread per output element = 1.4 ms for the discriminator; one thread per (row, col) with scalar loads at a 36-byte
+// stride and 2-byte stores = 0.24 ms at 0.5 TB/s; the traffic is ~0.1 ms.)
+constexpr int kPackTile = 32;
+constexpr int kPackSmemFloats = kPackTile * (kPackTile * 16 + 1);
+__device__ __forceinline__ void pack_tile(const PackP& p, int tile, float* sm) {
+  const int tiles_c = (p.cols_pad + kPackTile - 1) / kPackTile;
+  const int row0 = (tile / tiles_c) * kPackTile, col0 = (tile % tiles_c) * kPackTile;
+  const int co0 = p.transpose ? col0 : row0, ci0 = p.transpose ? row0 : col0;
+  const int KK = p.KK, run = kPackTile * KK, stride = run + 1;
+  const int n_co = p.Co - co0, n_ci = p.Ci - ci0;   // valid extent of the tile (may be <= 0 in the padding)
+  // a warp streams one co row (32*KK contiguous floats) at a time, KK loads of 128 bytes kept in flight together
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lim = n_ci * KK;
+#pragma unroll
+    for (int j = 0; j < kPackTile / 8; ++j) {
+      const int co_l = warp + 8 * j;
+      const float* src = p.w + (static_cast<long long>(co0 + co_l) * p.Ci + ci0) * KK;
+      // all 16 loads are issued unconditionally (invalid ones re-read p.w[0]) so that they stay in flight together:
+      // with predicated loads the compiler serialised load -> use, one DRAM latency per 128 bytes
+      float v[16];
+      uint32_t ok = 0;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int r = lane + 32 * m;
+        const bool in = (m < KK) && (co_l < n_co) && (r < lim);
+        ok |= static_cast<uint32_t>(in) << m;
+        v[m] = __ldg(in ? src + r : p.w);
+      }
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        if (m < KK) sm[co_l * stride + lane + 32 * m] = ((ok >> m) & 1u) ? v[m] * p.scale : 0.f;
+    }
+  }
+  __syncthreads();
+  const int item = threadIdx.x & 127, row_l = item >> 2, cg = item & 3;
+  const int row = row0 + row_l, col = col0 + cg * 8;
+  if (row >= p.rows_pad || col >= p.cols_pad) return;
   const long long per_slot = static_cast<long long>(p.rows_pad) * p.cols_pad;
-  const bool in_range = i < per_slot;
-  const int col = in_range ? static_cast<int>(i % p.cols_pad) : 0;
-  const int row = in_range ? static_cast<int>(i / p.cols_pad) : 0;
-  const int co = p.transpose ? col : row, ci = p.transpose ? row : col;
-  const bool valid = in_range && co < p.Co && ci < p.Ci;
-  const float* src = p.w + (static_cast<long long>(co) * p.Ci + ci) * p.KK;
-  for (int k = 0; k < p.KK; ++k) sm[k * blockDim.x + threadIdx.x] = valid ? __ldg(src + k) * p.scale : 0.f;
-  if (!in_range) return;
-  for (int slot = 0; slot < p.n_slots; ++slot) {
-    float v = 0.f;
+  for (int slot = threadIdx.x >> 7; slot < p.n_slots; slot += 2) {
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int t = p.taps[slot][j];   // warp-uniform
-      if (t >= 0) v += sm[t * blockDim.x + threadIdx.x];
+      const int t = p.taps[slot][j];   // block-uniform
+      if (t >= 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int co_l = p.transpose ? cg * 8 + e : row_l, ci_l = p.transpose ? row_l : cg * 8 + e;
+          v[e] += sm[co_l * stride + ci_l * KK + t];
+        }
+      }
     }
-    p.out[pack_dst(p, slot, row, col, slot * per_slot + i)] = __float2bfloat16_rn(v);
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]), o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]), o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]), o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]), o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(p.out + pack_dst(p, slot, row, col, slot * per_slot + static_cast<long long>(row) * p.cols_pad + col)) = o;
   }
 }
+static int pack_blocks(int rows_pad, int cols_pad) {
+  return ((rows_pad + kPackTile - 1) / kPackTile) * ((cols_pad + kPackTile - 1) / kPackTile);
+}
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackP p) {
-  __shared__ float sm[16 * 256];
-  pack_body(p, blockIdx.x * 256LL + threadIdx.x, sm);
+  extern __shared__ float pack_sm[];
+  pack_tile(p, blockIdx.x, pack_sm);
 }
 // All weight tensors of a network in one launch: entries[e] = PackP + first block; a block finds its entry by
 // scanning the (<= 128-entry) table.
@@ -172,17 +215,22 @@ struct PackEntry {
   int block_start;
 };
 __global__ void __launch_bounds__(256) pack_batched_kernel(const PackEntry* __restrict__ entries, int n_entries) {
-  __shared__ float sm[16 * 256];
-  __shared__ PackP sp;
-  __shared__ int s_start;
-  if (threadIdx.x == 0) {
-    int e = 0;
-    while (e + 1 < n_entries && static_cast<int>(blockIdx.x) >= entries[e + 1].block_start) ++e;
-    s_start = entries[e].block_start;
-    sp = entries[e].p;
+  extern __shared__ float pack_sm[];
+  __shared__ __align__(16) PackP sp;
+  // every thread runs the same binary search (broadcast loads; a linear scan by one thread cost more than the tile's
+  // work), then the block copies the entry cooperatively
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (static_cast<int>(blockIdx.x) >= __ldg(&entries[mid].block_start)) lo = mid;
+    else hi = mid - 1;
   }
+  const int start = __ldg(&entries[lo].block_start);
+  static_assert(sizeof(PackP) % 4 == 0, "PackP is copied word by word");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&entries[lo].p);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(PackP) / 4); i += 256) reinterpret_cast<uint32_t*>(&sp)[i] = __ldg(src + i);
   __syncthreads();
-  pack_body(sp, (blockIdx.x - s_start) * 256LL + threadIdx.x, sm);
+  pack_tile(sp, blockIdx.x - start, pack_sm);
 }
 
 // dw[co][ci][r*3+s] += sum_{a,c} folded[(a*2+c)*4 + dyi_a(r)*2 + dxi_c(s)][co][ci]   (sub-pixel un-fold)
@@ -239,7 +287,28 @@ __global__ void __launch_bounds__(256)
   const float coef = gscale * (max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f);
   const float c1 = 1.f - powf(b1, t), c2s = sqrtf(1.f - powf(b2, t));
   const float step_size = lr / c1;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+  // 16-byte accesses (the flat buffers are 16-byte aligned and padded to multiples of four elements); a scalar
+  // tail covers any other caller
+  const long long n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) ? 0 : n / 4;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    const float gs[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+    float* mm = reinterpret_cast<float*>(&m4);
+    float* vv = reinterpret_cast<float*>(&v4);
+    float* pp = reinterpret_cast<float*>(&p4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mm[j] = b1 * mm[j] + (1.f - b1) * gs[j];
+      vv[j] = b2 * vv[j] + (1.f - b2) * gs[j] * gs[j];
+      pp[j] -= step_size * mm[j] / (sqrtf(vv[j]) / c2s + eps);
+    }
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     const float gi = g[i] * coef;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -290,9 +359,13 @@ int dfgan_pack_weights(const float* w, void* out, int Co, int Ci, int KK, int tr
   p.rows_pad = rows_pad, p.cols_pad = cols_pad, p.n_slots = n_slots, p.scale = scale, p.image = image;
   for (int s = 0; s < kPackSlots; ++s)
     for (int j = 0; j < 4; ++j) p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
-  if (KK > 16) return DFGAN_E_SHAPE;
-  const long long total = static_cast<long long>(rows_pad) * cols_pad;
-  pack_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, STREAM(st)>>>(p);
+  if (KK > 16 || (cols_pad & 7)) return DFGAN_E_SHAPE;
+  const int smem = static_cast<int>(kPackSmemFloats * sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  // three 66 KB blocks per SM need the large shared-memory carveout (the default heuristic gave one block per SM)
+  cudaFuncSetAttribute(pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  pack_kernel<<<pack_blocks(rows_pad, cols_pad), 256, smem, STREAM(st)>>>(p);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;
@@ -316,15 +389,19 @@ int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, in
   for (int s = 0; s < kPackSlots; ++s)
     for (int j = 0; j < 4; ++j) e.p.taps[s][j] = s < n_slots ? slot_taps[s * 4 + j] : -1;
   e.block_start = block_start;
-  if (KK > 16) return DFGAN_E_SHAPE;
+  if (KK > 16 || (cols_pad & 7)) return DFGAN_E_SHAPE;
   *static_cast<PackEntry*>(entry_out) = e;
-  const long long total = static_cast<long long>(rows_pad) * cols_pad;
-  return static_cast<int>((total + 255) / 256);
+  return pack_blocks(rows_pad, cols_pad);
 }
 
 int dfgan_pack_batched(const void* entries_dev, int n_entries, int total_blocks, dfgan_stream_t st) {
   if (!entries_dev || n_entries < 1 || total_blocks < 1) return DFGAN_E_ARG;
-  pack_batched_kernel<<<total_blocks, 256, 0, STREAM(st)>>>(static_cast<const PackEntry*>(entries_dev), n_entries);
+  const int smem = static_cast<int>(kPackSmemFloats * sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(pack_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaFuncSetAttribute(pack_batched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  pack_batched_kernel<<<total_blocks, 256, smem, STREAM(st)>>>(static_cast<const PackEntry*>(entries_dev), n_entries);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;
