@@ -44,6 +44,7 @@ _TABLE: dict = {
     "dfgan_pack_batched": [P, I, I, P],
     "dfgan_unfold_subpixel_wgrad": [P, P, I, I, P],
     "dfgan_sqnorm": [P, L, P, P],
+    "dfgan_sqnorm_det": [P, L, P, P, I, P],
     "dfgan_adam_step": [P, P, P, P, L, P, P, F, F, F, F, F, F, P],
     "dfgan_conv2d_f32_fprop": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],

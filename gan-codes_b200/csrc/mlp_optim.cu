@@ -323,6 +323,45 @@ __global__ void unfold_kernel(const float* __restrict__ folded, float* __restric
 }
 
 // ------------------------------------------------------------------------------------ clip + Adam
+// Deterministic variant: every block writes its partial sum (fixed in-block order) to scratch[blockIdx.x]; the block
+// that finishes last adds all partials in index order.  The result does not depend on the order in which blocks
+// run, so every data-parallel rank derives bit-identical clip coefficients from the all-reduced gradient (with
+// float atomics the ranks' parameters drifted apart by ulps whenever the clip was active).
+// scratch: gridDim.x floats + one zero-initialised uint counter (reset by the last block).
+__global__ void __launch_bounds__(256) sqnorm_det_kernel(const float* __restrict__ g, long long n, float* out,
+                                                         float* scratch) {
+  __shared__ float red[8];
+  __shared__ bool last;
+  float acc = 0.f;
+  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 4; i < n; i += gridDim.x * 1024LL) {
+    if (i + 3 < n) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(g + i));
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (long long j = i; j < n; ++j) acc += g[j] * g[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + gridDim.x);
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    scratch[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned int i = 0; i < gridDim.x; ++i) s += __ldcg(scratch + i);
+    *out += s;
+    *counter = 0u;
+  }
+}
 __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* out) {
   __shared__ float red[8];
   float acc = 0.f;
@@ -493,6 +532,17 @@ int dfgan_sqnorm(const float* g, int64_t n, float* out, dfgan_stream_t st) {
   long long blocks = (n + 1023) / 1024;
   if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
   sqnorm_kernel<<<static_cast<int>(blocks), 256, 0, STREAM(st)>>>(g, n, out);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_sqnorm_det(const float* g, int64_t n, float* out, float* scratch, int scratch_floats, dfgan_stream_t st) {
+  if (!g || !out || !scratch || n < 1 || (reinterpret_cast<uintptr_t>(g) & 15)) return DFGAN_E_ARG;
+  long long blocks = (n + 1023) / 1024;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+  if (scratch_floats < blocks + 1) return DFGAN_E_ARG;
+  sqnorm_det_kernel<<<static_cast<int>(blocks), 256, 0, STREAM(st)>>>(g, n, out, scratch);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;

@@ -55,6 +55,8 @@ class FlatState:
         self.n_real = sum(p.numel() for _, p in named)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
         self.sumsq = torch.zeros(1, device=dev, dtype=F32)
+        self.norm_scratch = torch.zeros(4 * torch.cuda.get_device_properties(dev).multi_processor_count + 8,
+                                        device=dev, dtype=F32)
         self.lr, self.betas, self.eps, self.clip = lr, betas, eps, clip
 
     def zero_grad(self) -> None:
@@ -69,7 +71,7 @@ class FlatState:
     def apply(self, world: int = 1) -> None:
         """global L2 norm -> clip -> Adam on the flat buffers (two kernels)."""
         self.sumsq.zero_()
-        K.sqnorm(self.grad, self.sumsq)
+        K.sqnorm_det(self.grad, self.sumsq, self.norm_scratch)   # bit-identical on every data-parallel rank
         self.step_count.add_(1)
         K.adam_step(self.flat, self.grad, self.m, self.v, self.sumsq, self.step_count, lr=self.lr,
                     gscale=1.0 / world, max_norm=self.clip, b1=self.betas[0], b2=self.betas[1], eps=self.eps)

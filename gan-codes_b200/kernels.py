@@ -267,6 +267,13 @@ def unfold_subpixel_wgrad(folded, dw):
     _call("dfgan_unfold_subpixel_wgrad", _p(folded), _p(dw), co, ci, _s())
 
 
+def sqnorm_det(g, out, scratch):
+    """out += sum(g^2) with a scheduling-independent (bit-reproducible) result; scratch: zero-initialised fp32 buffer
+    of at least 4 * #SMs + 1 elements owned by the caller."""
+    assert g.dtype == F32 and g.is_contiguous() and out.dtype == F32 and scratch.dtype == F32
+    _call("dfgan_sqnorm_det", _p(g), g.numel(), _p(out), _p(scratch), scratch.numel(), _s())
+
+
 def sqnorm(g, out):
     assert g.dtype == F32 and g.is_contiguous() and out.dtype == F32
     _call("dfgan_sqnorm", _p(g), g.numel(), _p(out), _s())

@@ -218,6 +218,10 @@ int dfgan_unfold_subpixel_wgrad(const float* folded, float* dw, int Co, int Ci, 
 /* *out += sum g^2 ; then clip (global L2 norm, max_norm) + Adam over a flat buffer.  step: device int (>= 1).
  * replaces: clip_grad_norm_ + Adam.step, deep_fusion_gan/model.py:42-43,195-197,208-210,226-228 */
 int dfgan_sqnorm(const float* g, int64_t n, float* out, dfgan_stream_t st);
+/* The same with a result that does not depend on block scheduling (per-block partials in scratch, summed in index
+ * order by the last block): data-parallel ranks must derive bit-identical clip coefficients.  scratch: at least
+ * 4 * #SMs + 1 floats, the last used word (a counter) zero before the first call. */
+int dfgan_sqnorm_det(const float* g, int64_t n, float* out, float* scratch, int scratch_floats, dfgan_stream_t st);
 int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* sumsq,
                     const int* step, float gscale, float max_norm, float lr, float b1, float b2, float eps,
                     dfgan_stream_t st);

@@ -456,6 +456,18 @@ def optim():
         e = _rel(p - pr.detach(), torch.zeros_like(p)) if False else ((p - pr.detach()).abs().max() / 4e-4).item()
         print(f"adam it{it}: max |dp| / lr = {e:.3e}, sumsq rel {abs(ss.item() - (gi ** 2).sum().item()) / (gi ** 2).sum().item():.2e}")
         ok &= e < 1e-2
+    # scheduling-independent norm (data-parallel ranks must derive bit-identical clip coefficients): same bits on
+    # every run, value within fp32 rounding of the fp64 sum
+    big = torch.randn(19_645_272, device="cuda") * 0.05
+    scratch = torch.zeros(4 * torch.cuda.get_device_properties(0).multi_processor_count + 8, device="cuda")
+    vals = []
+    for _ in range(6):
+        ss = torch.zeros(1, device="cuda")
+        K.sqnorm_det(big, ss, scratch)
+        vals.append(ss.item())
+    ref = (big.double() ** 2).sum().item()
+    print(f"sqnorm_det: {len(set(vals))} distinct value(s) over 6 runs, rel err {abs(vals[0] - ref) / ref:.2e}")
+    ok &= len(set(vals)) == 1 and abs(vals[0] - ref) / ref < 1e-5
     return ok
 
 
