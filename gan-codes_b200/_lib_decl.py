@@ -46,6 +46,9 @@ _TABLE: dict = {
     "dfgan_sqnorm": [P, L, P, P],
     "dfgan_sqnorm_det": [P, L, P, P, I, P],
     "dfgan_adam_step": [P, P, P, P, L, P, P, F, F, F, F, F, F, P],
+    "dfgan_gblock_small_grads": [P, P, P, P, P, P, I, P],
+    "dfgan_d_hinge": [P, P, P, I, P],
+    "dfgan_gp_coef": [P, P, P, I, P],
     "dfgan_conv2d_f32_fprop": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],

@@ -540,6 +540,70 @@ static inline int pick_ppb(int N, int HW, int C) {
   return ppb;
 }
 
+
+// ------------------------------------------------------------------------------------ small fused scalar math
+// (each of these replaced 5-25 two-microsecond torch launches that sat on the critical path of the CUDA graph)
+//
+// Generator block, small parameter gradients from the per-channel sums cs[c] = sum_pixels g_z[., c]
+// (generator/residual_block.py:47,59 and :29-33):  d conv_2.bias += gamma * cs ;  d scale_conv.bias += cs ;
+// d gamma += <cs, conv_2.bias>   (the bias part of d/dgamma <g_z, gamma * (conv_2(h) + bias)>)
+__global__ void __launch_bounds__(256)
+    gblock_small_grads_kernel(const float* __restrict__ cs, const float* __restrict__ gamma,
+                              const float* __restrict__ bias2, float* g_bias2, float* g_gamma, float* g_sbias, int C) {
+  __shared__ float red[8];
+  float part = 0.f;
+  const float gm = __ldg(gamma);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float v = __ldg(cs + c);
+    g_bias2[c] += gm * v;
+    if (g_sbias) g_sbias[c] += v;
+    part += v * __ldg(bias2 + c);
+  }
+  block_reduce1(part, red, g_gamma, 1.f);
+}
+
+// Discriminator hinge loss and its logit cotangents (deep_fusion_gan/model.py:175-189) from the concatenated
+// logits [real (B) ; mismatched (B-1) ; fake (B)]:
+//   loss = mean relu(1 - real) + (mean relu(1 + fake) + mean relu(1 + mis)) / 2
+//   g[real] = -(real < 1) / B ; g[mis] = (mis > -1) / (2 (B-1)) ; g[fake] = (fake > -1) / (2 B)
+__global__ void __launch_bounds__(256) d_hinge_kernel(const float* __restrict__ lg, float* loss, float* g, int B) {
+  __shared__ float red[8];
+  float part = 0.f;
+  const int n = 3 * B - 1;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = __ldg(lg + i);
+    if (i < B) {
+      part += fmaxf(1.f - v, 0.f) / B;
+      g[i] = v < 1.f ? -1.f / B : 0.f;
+    } else if (i < 2 * B - 1) {
+      part += 0.5f * fmaxf(1.f + v, 0.f) / (B - 1);
+      g[i] = v > -1.f ? 0.5f / (B - 1) : 0.f;
+    } else {
+      part += 0.5f * fmaxf(1.f + v, 0.f) / B;
+      g[i] = v > -1.f ? 0.5f / B : 0.f;
+    }
+  }
+  if (threadIdx.x == 0) *loss = 0.f;
+  block_reduce1(part, red, loss, 1.f);
+}
+
+// MA-GP loss and the per-sample coefficient of its gradient (deep_fusion_gan/model.py:82-85, 203):
+//   n_b = sqrt(sq_b + 1e-8) ; loss = 2 * mean(clamp(n_b, 0, 10)^6) ; coef_b = (12 / B) n_b^4 [n_b <= 10]
+__global__ void __launch_bounds__(256) gp_coef_kernel(const float* __restrict__ sq, float* loss, float* coef, int B) {
+  __shared__ float red[8];
+  float part = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const float n = sqrtf(__ldg(sq + i) + 1e-8f);
+    const float nc = fminf(fmaxf(n, 0.f), 10.f);
+    const float n2 = nc * nc;
+    part += 2.f * n2 * n2 * n2 / B;
+    const float m2 = n * n;
+    coef[i] = n <= 10.f ? (12.f / B) * m2 * m2 : 0.f;
+  }
+  if (threadIdx.x == 0) *loss = 0.f;
+  block_reduce1(part, red, loss, 1.f);
+}
+
 }  // namespace dfgan
 
 using namespace dfgan;
@@ -699,6 +763,32 @@ int dfgan_head_out_bwd(const float* g_logit, const void* hid, const void* act, c
   head_out_bwd_kernel<<<blocks_for(16 * Ch, 128), 128, 0, STREAM(st)>>>(
       g_logit, static_cast<const __nv_bfloat16*>(hid), static_cast<const __nv_bfloat16*>(act), w2,
       static_cast<__nv_bfloat16*>(g_hid), dw2, B, Ch, 0.2f);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+
+int dfgan_gblock_small_grads(const float* cs, const float* gamma, const float* bias2, float* g_bias2, float* g_gamma,
+                             float* g_sbias, int C, dfgan_stream_t st) {
+  if (!cs || !gamma || !bias2 || !g_bias2 || !g_gamma || C < 1) return DFGAN_E_ARG;
+  gblock_small_grads_kernel<<<1, 256, 0, STREAM(st)>>>(cs, gamma, bias2, g_bias2, g_gamma, g_sbias, C);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_d_hinge(const float* logits, float* loss, float* g_logits, int B, dfgan_stream_t st) {
+  if (!logits || !loss || !g_logits || B < 2) return DFGAN_E_ARG;
+  d_hinge_kernel<<<1, 256, 0, STREAM(st)>>>(logits, loss, g_logits, B);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_gp_coef(const float* sq, float* loss, float* coef, int B, dfgan_stream_t st) {
+  if (!sq || !loss || !coef || B < 1) return DFGAN_E_ARG;
+  gp_coef_kernel<<<1, 256, 0, STREAM(st)>>>(sq, loss, coef, B);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;

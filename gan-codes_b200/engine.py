@@ -124,10 +124,10 @@ class DFGANTrainer:
         sent3 = torch.cat((sent, sent[1:b], sent), dim=0)
         hctx: dict = {}
         lg = dnet.head_forward(dpk, dp, emb3, sent3, hctx)
-        real, mis, fk = lg[:b], lg[b:2 * b - 1], lg[2 * b - 1:]
-        loss = torch.relu(1.0 - real).mean() + 0.5 * (torch.relu(1.0 + fk).mean() + torch.relu(1.0 + mis).mean())
-        g_lg = torch.cat((-(real < 1.0).to(F32) / b, 0.5 * (mis > -1.0).to(F32) / (b - 1),
-                          0.5 * (fk > -1.0).to(F32) / b))
+        # hinge loss over [real ; mismatched ; fake] and its logit cotangents: one launch (:175-189)
+        loss, g_lg = torch.empty(1, device=lg.device, dtype=F32), torch.empty_like(lg)
+        K.d_hinge(lg, loss, g_lg, b)
+        loss = loss[0]
         self.ds.zero_grad()
         ge, _ = dnet.head_backward(dpk, dp, hctx, g_lg, self.ds.grads, False)
         g_emb = torch.cat((ge[:b], ge[2 * b - 1:]), dim=0)
@@ -154,10 +154,11 @@ class DFGANTrainer:
         sq = torch.zeros(b, device=gx.device, dtype=F32)
         K.rowsq(gx, sq)
         K.rowsq(g_sent, sq)
-        n = torch.sqrt(sq + 1e-8)                                   # deep_fusion_gan/model.py:82
-        nc = torch.clamp(n, 0, 10)                                  # :85
-        loss = 2.0 * torch.mean(nc ** 6)                            # :203
-        coef = (12.0 / b) * n ** 4 * (n <= 10.0).to(F32)            # d loss / d g_b = coef_b * g_b (G11)
+        # n = sqrt(sq + 1e-8) (:82), clamp(n, 0, 10) (:85), loss = 2 mean(n^6) (:203) and d loss / d g_b = coef_b * g_b
+        # with coef_b = (12 / B) n_b^4 [n_b <= 10] (G11): one launch
+        loss, coef = torch.empty(1, device=sq.device, dtype=F32), torch.empty_like(sq)
+        K.gp_coef(sq, loss, coef)
+        loss = loss[0]
         self.ds.zero_grad()
         t_emb = dnet.trunk_tangent(dpk, dp, tctx, cots, gx, coef, self.ds.grads)
         dnet.head_tangent(dpk, dp, hctx, cots, dnet.embeds_to_nchw(t_emb), g_sent, coef, self.ds.grads)

@@ -258,6 +258,8 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
     g_z = e(*z.shape)
     co.conv_run([g_t], co.taps_3x3_dgrad(pk.c_last), pk.wo_d, pk.c_last, g_z, mask_src=z)
     mlp.d_tab.zero_()
+    cs_all = torch.zeros(sum(c2_ for (_, _, c2_, _) in pk.plan), device=dev, dtype=F32)   # per-block channel sums
+    cs_off = 0
     for i in range(len(pk.plan) - 1, -1, -1):
         (p, c1, c2, sc), b = pk.plan[i], pk.blocks[i]
         z_prev, a12, h1, a34 = ctx["saved"][i]
@@ -271,13 +273,16 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
             co.wgrad_run([a34], TAPS3_ID, g_z, grads[p + ".conv_2.weight"],
                          _oihw_strides(params[p + ".conv_2.weight"]), scale_dev=gamma)
         # shortcut branch: 2x2 sum (backward of the nearest upsample) + per-channel sums of g_z
-        cs = torch.zeros(c2, device=dev, dtype=F32)
+        cs = cs_all[cs_off:cs_off + c2]
+        cs_off += c2
         pooled = e(n, h, h, c2) if up else None
         K.pool(g_z, pooled, shift=1 if up else 0, scale=1.0, colsum=cs)
         if not up:
             pooled = g_z
-        grads[p + ".conv_2.bias"].addcmul_(cs, gamma)
-        grads[p + ".gamma"].add_((cs * params[p + ".conv_2.bias"]).sum())
+        # conv_2.bias, scale_conv.bias and the bias part of the gate gradient: one small launch off the main chain
+        with co.side(n_side + 2, dev):
+            K.gblock_small_grads(cs, gamma, params[p + ".conv_2.bias"], grads[p + ".conv_2.bias"],
+                                 grads[p + ".gamma"], grads[p + ".scale_conv.bias"] if sc else None)
         # affine 3/4 backward -> gradient at conv_1's output, gamma-gate dot product, conv_1 bias gradient
         g_h1 = e(n, hh, hh, c2)
         K.affine2_bwd(q, h1, g_h1, mlp.tables(p, 3), mlp.tables(p, 3, mlp.d_tab), mlp.T, gscale=gamma,
@@ -299,7 +304,6 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
             with co.side(n_side + 1, dev):
                 co.wgrad_run([a12], TAPS3_ID, g_h1, grads[p + ".conv_1.weight"], _oihw_strides(w1))
         if sc:
-            grads[p + ".scale_conv.bias"].add_(cs)
             t = e(n, h, h, c1)
             co.conv_run([pooled], co.taps_1x1(), b["ws_d"], c1, t)
             with co.side(n_side + 2, dev):

@@ -267,6 +267,28 @@ def unfold_subpixel_wgrad(folded, dw):
     _call("dfgan_unfold_subpixel_wgrad", _p(folded), _p(dw), co, ci, _s())
 
 
+def gblock_small_grads(cs, gamma, bias2, g_bias2, g_gamma, g_sbias=None):
+    """conv_2.bias / scale_conv.bias / gate gradients of a generator block from the per-channel cotangent sums."""
+    for t in (cs, gamma, bias2, g_bias2, g_gamma):
+        assert t.dtype == F32 and t.is_contiguous()
+    assert g_sbias is None or (g_sbias.dtype == F32 and g_sbias.is_contiguous())
+    _call("dfgan_gblock_small_grads", _p(cs), _p(gamma), _p(bias2), _p(g_bias2), _p(g_gamma), _p(g_sbias),
+          cs.numel(), _s())
+
+
+def d_hinge(logits, loss, g_logits, batch):
+    """logits fp32 [3B-1] = [real; mismatched; fake] -> loss (1 element, overwritten) and d loss / d logits."""
+    assert logits.dtype == F32 and logits.is_contiguous() and logits.numel() == 3 * batch - 1
+    assert g_logits.dtype == F32 and g_logits.numel() == logits.numel() and loss.dtype == F32
+    _call("dfgan_d_hinge", _p(logits), _p(loss), _p(g_logits), batch, _s())
+
+
+def gp_coef(sq, loss, coef):
+    """sq fp32 [B] -> MA-GP loss (1 element, overwritten) and the per-sample coefficient of its gradient."""
+    assert sq.dtype == F32 and coef.dtype == F32 and sq.numel() == coef.numel() and loss.dtype == F32
+    _call("dfgan_gp_coef", _p(sq), _p(loss), _p(coef), sq.numel(), _s())
+
+
 def sqnorm_det(g, out, scratch):
     """out += sum(g^2) with a scheduling-independent (bit-reproducible) result; scratch: zero-initialised fp32 buffer
     of at least 4 * #SMs + 1 elements owned by the caller."""

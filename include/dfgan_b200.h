@@ -226,6 +226,19 @@ int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, con
                     const int* step, float gscale, float max_norm, float lr, float b1, float b2, float eps,
                     dfgan_stream_t st);
 
+/* Small fused scalar math of the training step (each replaces a chain of tiny elementwise launches).
+ * dfgan_gblock_small_grads: generator block, from cs[c] = sum over pixels of the block's output cotangent:
+ *   g_bias2 += gamma * cs (conv_2.bias), g_sbias += cs (scale_conv.bias, may be NULL), g_gamma += <cs, bias2>
+ *   (generator/residual_block.py:29-33,47,59).
+ * dfgan_d_hinge: logits = [real (B) ; mismatched (B-1) ; fake (B)] -> hinge loss and d loss / d logits
+ *   (deep_fusion_gan/model.py:175-189).
+ * dfgan_gp_coef: sq[b] = |d logit / d (image, sentence)|^2 -> MA-GP loss 2 mean(clamp(sqrt(sq + 1e-8), 0, 10)^6) and
+ *   coef[b] = (12 / B) n_b^4 [n_b <= 10]  (deep_fusion_gan/model.py:82-85, 203). */
+int dfgan_gblock_small_grads(const float* cs, const float* gamma, const float* bias2, float* g_bias2, float* g_gamma,
+                             float* g_sbias, int C, dfgan_stream_t st);
+int dfgan_d_hinge(const float* logits, float* loss, float* g_logits, int B, dfgan_stream_t st);
+int dfgan_gp_coef(const float* sq, float* loss, float* coef, int B, dfgan_stream_t st);
+
 /* ---------------------------------------------------------------------------------------------------------
  * fp32 precision tier (north_star: "1e-4 for fp32 / tf32-off"): plain CUDA-core convolution on the reference's own
  * layouts -- x [N,Cin,H,W], w [Cout,Cin,KH,KW], y [N,Cout,OH,OW], all fp32 contiguous, stride 1 or 2, KH*KW <= 16.
