@@ -225,15 +225,19 @@ __global__ void __launch_bounds__(kPwThreads, 4)
 // out[n,i,j,c] = scale * sum_{a,b < f} x[n, f*i+a, f*j+b, c]  (f = 1 << shift);  colsum[c] += cs * sum x
 // avg_pool2d (discriminator/residual_block.py:27) with scale .25; backward of F.interpolate
 // (generator/model.py:40) with scale 1; shift 0 degenerates to a copy + column sum.
+// SHIFT is a template parameter so that the copy + column-sum form (SHIFT = 0, one load per pixel) can keep four
+// pixels in flight per thread without the register cost of the four-tap form.
+template <int SHIFT, int U>
 __global__ void __launch_bounds__(kPwThreads, 4)
     pool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, float* colsum,
-                const float* cs_dev, float cs_imm, int Ho, int Wo, int C, int shift, float scale,
-                int pix_per_block) {
+                const float* cs_dev, float cs_imm, int Ho, int Wo, int C, float scale, int pix_per_block) {
+  constexpr int shift = SHIFT;
+  constexpr int NQ = SHIFT ? 4 : 1;
   __shared__ float red[kPwThreads * 8];
   const int n = blockIdx.y;
   const int tpp = C >> 3;
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp, ppi = kPwThreads / tpp;
-  const int f = 1 << shift;
+  constexpr int f = 1 << shift;
   const int Wi = Wo << shift;
   const long long ibase = static_cast<long long>(n) * (Ho << shift) * Wi * C;
   const long long obase = static_cast<long long>(n) * Ho * Wo * C;
@@ -241,20 +245,18 @@ __global__ void __launch_bounds__(kPwThreads, 4)
   const int HW = Ho * Wo;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(HW, p0 + pix_per_block);
-  constexpr int U = 1;
   for (int pb = p0 + pl; pb < p1; pb += U * ppi) {
-    bf8 v[U][4];
+    bf8 v[U][NQ];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int p = pb + u * ppi;
       if (p < p1) {
         const int i = p / Wo, j = p - i * Wo;
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < f; ++a)
 #pragma unroll
-          for (int b = 0; b < 2; ++b)
-            if (a < f && b < f)
-              v[u][a * 2 + b] = ld8(x + ibase + (static_cast<long long>(f * i + a) * Wi + (f * j + b)) * C + cg * 8);
+          for (int b = 0; b < f; ++b)
+            v[u][a * f + b] = ld8(x + ibase + (static_cast<long long>(f * i + a) * Wi + (f * j + b)) * C + cg * 8);
       }
     }
 #pragma unroll
@@ -263,11 +265,10 @@ __global__ void __launch_bounds__(kPwThreads, 4)
       if (p >= p1) continue;
       bf8 s{};
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if ((q >> 1) < f && (q & 1) < f) {
+      for (int q = 0; q < NQ; ++q) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s.v[k] += v[u][q].v[k];
-        }
+        for (int k = 0; k < 8; ++k) s.v[k] += v[u][q].v[k];
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         acc.v[k] += s.v[k];
@@ -361,9 +362,13 @@ __global__ void __launch_bounds__(kPwThreads)
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
+        // unconditional loads from clamped coordinates (all 27 stay in flight), zeroed afterwards where the tap
+        // falls into the padding
         const int hh = h + r - 1, ww = w + s - 1;
         const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
-        v[ci * 9 + r * 3 + s] = in ? sc * __ldg(base + (static_cast<long long>(ci) * H + hh) * W + ww) : 0.f;
+        const int hc = min(max(hh, 0), H - 1), wc = min(max(ww, 0), W - 1);
+        const float x = __ldg(base + (static_cast<long long>(ci) * H + hc) * W + wc);
+        v[ci * 9 + r * 3 + s] = in ? sc * x : 0.f;
       }
 #pragma unroll
   for (int i = 27; i < 32; ++i) v[i] = 0.f;
@@ -646,9 +651,15 @@ int dfgan_pool(const void* x, void* out, float* colsum, const float* cs_dev, flo
                int Wo, int C, int shift, float scale, dfgan_stream_t st) {
   if (!x || (!out && !colsum) || !c_ok(C) || shift < 0 || shift > 1) return DFGAN_E_ARG;
   const int ppb = pick_ppb(N, Ho * Wo, C);
-  pool_kernel<<<dim3((Ho * Wo + ppb - 1) / ppb, N), kPwThreads, 0, STREAM(st)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), colsum, cs_dev, cs_imm, Ho, Wo,
-      C, shift, scale, ppb);
+  const dim3 grid((Ho * Wo + ppb - 1) / ppb, N);
+  if (shift)
+    pool_kernel<1, 1><<<grid, kPwThreads, 0, STREAM(st)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                           static_cast<__nv_bfloat16*>(out), colsum, cs_dev, cs_imm,
+                                                           Ho, Wo, C, scale, ppb);
+  else
+    pool_kernel<0, 4><<<grid, kPwThreads, 0, STREAM(st)>>>(static_cast<const __nv_bfloat16*>(x),
+                                                           static_cast<__nv_bfloat16*>(out), colsum, cs_dev, cs_imm,
+                                                           Ho, Wo, C, scale, ppb);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;
