@@ -1199,6 +1199,8 @@ struct Halo2K {
   int n_src, pitch, hal_h, n_chunks;
   uint32_t a_part_bytes, a_stage_bytes, b_bytes;
   int n_a_stages, n_b_stages, n_acc;
+  int pair;                 // 1: a CTA works on TWO pixel tiles per pipeline step; both reuse every weight tile it loads
+  uint32_t a_tile_bytes;    // halo tiles of one pixel tile inside an A stage (a_stage_bytes = (1 + pair) * a_tile_bytes)
   uint32_t a_tap_off16[DFGAN_MAX_TAPS];
   long long w_tap_stride, w_chunk_stride;   // bytes between taps / 64-channel chunks of the packed image
   const uint8_t* wimg;
@@ -1256,22 +1258,27 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     const uint32_t txa = static_cast<uint32_t>(hp.n_src) * hp.hal_h * hp.pitch * 128u;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    // pair mode: the CTA's tiles k and k+1 of its sequence (tile, tile + gridDim.x) form one pipeline step
+    const int step = (hp.pair ? 2 : 1) * static_cast<int>(gridDim.x);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += step) {
+      const int n_in_step = (hp.pair && tile + static_cast<int>(gridDim.x) < p.total_tiles) ? 2 : 1;
       const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
-      const int tw = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int n = mt / p.tiles_h;
       const uint8_t* wbase = hp.wimg + static_cast<long long>(nt) * p.n_tile * 128;
       for (int c = 0; c < hp.n_chunks; ++c) {
         wait_bounded(&emptyA[sa], pa ^ 1);
-        if (leader) mbar_expect_tx(&fullA[sa], txa);
-        uint8_t* dst = sA + static_cast<size_t>(sa) * hp.a_stage_bytes;
-        for (int s = 0; s < hp.n_src; ++s) {
-          if (leader)
-            tma_load_4d(dst + static_cast<size_t>(s) * hp.a_part_bytes, &maps.a[s], &fullA[sa], c * 64,
-                        (tw << 3) + hp.dx_min[s], (th << 4) + hp.dy_min[s], n);
+        if (leader) mbar_expect_tx(&fullA[sa], txa * n_in_step);
+        for (int j = 0; j < n_in_step; ++j) {
+          int mt = (tile + j * static_cast<int>(gridDim.x)) / p.n_tiles_n;
+          const int tw = mt % p.tiles_w;
+          mt /= p.tiles_w;
+          const int th = mt % p.tiles_h;
+          const int n = mt / p.tiles_h;
+          uint8_t* dst = sA + static_cast<size_t>(sa) * hp.a_stage_bytes + static_cast<size_t>(j) * hp.a_tile_bytes;
+          for (int s = 0; s < hp.n_src; ++s) {
+            if (leader)
+              tma_load_4d(dst + static_cast<size_t>(s) * hp.a_part_bytes, &maps.a[s], &fullA[sa], c * 64,
+                          (tw << 3) + hp.dx_min[s], (th << 4) + hp.dy_min[s], n);
+          }
         }
         __syncwarp();
         if (++sa == hp.n_a_stages) sa = 0, pa ^= 1;
@@ -1297,13 +1304,20 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int step = (hp.pair ? 2 : 1) * static_cast<int>(gridDim.x);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += step) {
+        const bool two = hp.pair && tile + static_cast<int>(gridDim.x) < p.total_tiles;
+        // accumulator slots follow the epilogue's per-tile rotation: the second tile of a pair takes the next slot
+        // (n_acc is even, so a pair never wraps between its two slots)
         wait_bounded(&tempty[acc], aphase ^ 1);
+        if (two) wait_bounded(&tempty[acc + 1], aphase ^ 1);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        const uint32_t d_tmem1 = d_tmem + static_cast<uint32_t>(p.n_tile);
         for (int c = 0; c < hp.n_chunks; ++c) {
           wait_bounded(&fullA[sa], pa);
           uint64_t ad0 = make_smem_desc(sA_u + static_cast<uint32_t>(sa) * hp.a_stage_bytes, 16, sbo_a, SWZ_128B);
           asm volatile("" : "+l"(ad0));
+          const uint64_t ad1 = ad0 + (hp.a_tile_bytes >> 4);
           for (int t = 0; t < p.n_taps; ++t) {
             wait_bounded(&fullB[sb], pb);
             tc_fence_after();
@@ -1312,6 +1326,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
             asm volatile("" : "+l"(bdesc));
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (c | t | k) != 0);
+            if (two) {
+              const uint64_t adesc1 = ad1 + hp.a_tap_off16[t];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem1, adesc1 + 2u * k, bdesc + 2u * k, p.idesc, (c | t | k) != 0);
+            }
             umma_commit(&emptyB[sb]);
             if (++sb == hp.n_b_stages) sb = 0, pb ^= 1;
           }
@@ -1320,6 +1339,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         }
         umma_commit(&tfull[acc]);
         if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
+        if (two) {
+          umma_commit(&tfull[acc]);
+          if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
+        }
       }
     }
     __syncwarp();
@@ -1414,10 +1437,21 @@ static bool plan_halo2(const dfgan_conv_desc* d, Halo2K& hp, int& n_tile, int& s
   hp.n_src = d->n_src, hp.n_chunks = d->Cin / 64;
   hp.pitch = 8 + ext_w, hp.hal_h = 16 + ext_h;
   hp.a_part_bytes = (static_cast<uint32_t>(hp.hal_h * hp.pitch * 128) + 1023u) & ~1023u;
-  hp.a_stage_bytes = hp.a_part_bytes * static_cast<uint32_t>(d->n_src);
+  hp.a_tile_bytes = hp.a_part_bytes * static_cast<uint32_t>(d->n_src);
   hp.b_bytes = static_cast<uint32_t>(n_tile) * 128u;
   hp.n_acc = n_tile <= 128 ? 4 : 2;
   const size_t cap = 220 * 1024, fixed = 1024 + 512;
+  // Pair mode: per 128-pixel tile a CTA streams taps * chunks weight tiles of n_tile x 64 (1.2 MB for a 3x3 C256
+  // layer against 92 KB of halo tiles), which makes the wide layers L2 -> shared-memory bandwidth bound (~6 TB/s,
+  // measured 730 TFLOP/s).  Two pixel tiles per pipeline step reuse every weight tile: half the weight traffic.
+  // Used when every CTA has at least two tiles anyway and the doubled halo stage still leaves 2 + 3 stages.
+  static const bool pair_off = getenv("DFGAN_NO_PAIR") != nullptr;
+  const long long tiles = static_cast<long long>((d->W + 7) / 8) * ((d->H + 15) / 16) * d->N * (d->Cout / n_tile);
+  // (only with four accumulator slots, n_tile <= 128: with two slots a pair occupies both and the epilogue no longer
+  // overlaps the next pair's MMAs -- measured 1166 -> 1125 TFLOP/s on 3x3 C256, against 917 -> 1049 on C128)
+  hp.pair = (!pair_off && d->Cout == n_tile && n_tile <= 128 && tiles >= num_sms() &&
+             fixed + 2 * (2 * hp.a_tile_bytes) + 3 * hp.b_bytes <= cap) ? 1 : 0;
+  hp.a_stage_bytes = hp.a_tile_bytes * (hp.pair ? 2u : 1u);
   // at least 2 halo stages and 3 weight stages; prefer a third halo stage, then as many weight stages as fit
   if (fixed + 2 * hp.a_stage_bytes + 3 * hp.b_bytes > cap) return false;
   hp.n_a_stages = (fixed + 3 * hp.a_stage_bytes + 4 * hp.b_bytes <= cap) ? 3 : 2;
@@ -1622,7 +1656,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
         int rc = make_map_nhwc(&maps.a[s], v, 64, h2.pitch, h2.hal_h, 1);
         if (rc) return rc;
       }
-      int grid = k.total_tiles;
+      int grid = h2.pair ? (k.total_tiles + 1) / 2 : k.total_tiles;
       const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
       if (grid > cap) grid = cap;
       k.col_split = (k.total_tiles <= 3 * grid) ? 1 : 0;
