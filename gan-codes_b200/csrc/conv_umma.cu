@@ -85,9 +85,7 @@ __device__ __forceinline__ void store_round_bf16x16(__nv_bfloat16* dst, float* v
   uint32_t u[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) u[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  d[0] = make_uint4(u[0], u[1], u[2], u[3]);
-  d[1] = make_uint4(u[4], u[5], u[6], u[7]);
+  stg256(dst, make_uint4(u[0], u[1], u[2], u[3]), make_uint4(u[4], u[5], u[6], u[7]));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     v[2 * i] = __uint_as_float(u[i] << 16);
@@ -100,9 +98,7 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float* v
   s0.z = pack_bf16x2(v[4], v[5]), s0.w = pack_bf16x2(v[6], v[7]);
   s1.x = pack_bf16x2(v[8], v[9]), s1.y = pack_bf16x2(v[10], v[11]);
   s1.z = pack_bf16x2(v[12], v[13]), s1.w = pack_bf16x2(v[14], v[15]);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  d[0] = s0;
-  d[1] = s1;
+  stg256(dst, s0, s1);
 }
 __device__ __forceinline__ void load_bf16x16(const __nv_bfloat16* src, float* v) {
   const uint4* sp = reinterpret_cast<const uint4*>(src);
@@ -132,14 +128,8 @@ struct EpiPre {
 };
 __device__ __forceinline__ void epi_prefetch(const ConvK& p, EpiPre& e, bool on, long long m_off, long long a_off) {
   if (!on) return;
-  if (p.mask_src) {
-    const uint4* sp = reinterpret_cast<const uint4*>(p.mask_src + m_off);
-    e.m0 = __ldg(sp), e.m1 = __ldg(sp + 1);
-  }
-  if (p.addend) {
-    const uint4* sp = reinterpret_cast<const uint4*>(p.addend + a_off);
-    e.a0 = __ldg(sp), e.a1 = __ldg(sp + 1);
-  }
+  if (p.mask_src) ldg256(p.mask_src + m_off, e.m0, e.m1);
+  if (p.addend) ldg256(p.addend + a_off, e.a0, e.a1);
 }
 // request the mask / addend rows of the chunk at tile column c (output column gcol) for this thread's pixel
 __device__ __forceinline__ void epi_pre_issue(const ConvK& p, EpiPre& e, bool valid, int gcol, int c, int n, int h,
