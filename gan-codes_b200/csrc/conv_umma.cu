@@ -116,6 +116,17 @@ __device__ __forceinline__ void load_f32x16(const float* src, float* v) {
     v[4 * i] = f.x, v[4 * i + 1] = f.y, v[4 * i + 2] = f.z, v[4 * i + 3] = f.w;
   }
 }
+// the same for 32-byte aligned rows (gamma/beta tables; dfgan_conv_run checks the alignment): two 256-bit loads
+__device__ __forceinline__ void load_f32x16_a32(const float* src, float* v) {
+  uint4 q[4];
+  ldg256(src, q[0], q[1]);
+  ldg256(src + 8, q[2], q[3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[4 * i] = __uint_as_float(q[i].x), v[4 * i + 1] = __uint_as_float(q[i].y);
+    v[4 * i + 2] = __uint_as_float(q[i].z), v[4 * i + 3] = __uint_as_float(q[i].w);
+  }
+}
 __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
@@ -205,12 +216,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
       if (p.post_mode == 2) {
         const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
         float ga[16], ba[16];
-        load_f32x16(p.tab_ga + t_off, ga);
-        load_f32x16(p.tab_ba + t_off, ba);
+        load_f32x16_a32(p.tab_ga + t_off, ga);
+        load_f32x16_a32(p.tab_ba + t_off, ba);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = lrelu(fmaf(ga[i], v[i], ba[i]), p.slope);
-        load_f32x16(p.tab_gb + t_off, ga);
-        load_f32x16(p.tab_bb + t_off, ba);
+        load_f32x16_a32(p.tab_gb + t_off, ga);
+        load_f32x16_a32(p.tab_bb + t_off, ba);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaf(ga[i], v[i], ba[i]);
       }
@@ -1525,6 +1536,15 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   if (!d->out && !d->aux && !d->out2 && !d->out_nchw) return DFGAN_E_ARG;
   if (d->post_mode < 0 || d->post_mode > 2 || (d->post_mode && !d->out2)) return DFGAN_E_ARG;
   if (d->post_mode == 2 && !(d->tab_ga && d->tab_ba && d->tab_gb && d->tab_bb)) return DFGAN_E_ARG;
+  // 256-bit accesses: table rows and every bf16 tensor the epilogue touches must be 32-byte aligned per 16 columns
+  if (d->post_mode == 2 && (((reinterpret_cast<uintptr_t>(d->tab_ga) | reinterpret_cast<uintptr_t>(d->tab_ba) |
+                              reinterpret_cast<uintptr_t>(d->tab_gb) | reinterpret_cast<uintptr_t>(d->tab_bb)) & 31) ||
+                            (d->tab_stride & 7)))
+    return DFGAN_E_ARG;
+  if (((reinterpret_cast<uintptr_t>(d->out) | reinterpret_cast<uintptr_t>(d->aux) | reinterpret_cast<uintptr_t>(d->out2) |
+        reinterpret_cast<uintptr_t>(d->mask_src) | reinterpret_cast<uintptr_t>(d->addend)) & 31) ||
+      ((d->out_sw | d->out_sh | d->out_sn | d->add_sw | d->add_sh | d->add_sn) & 15))
+    return DFGAN_E_ARG;
   if (d->out_nchw && (d->co_valid < 1 || d->co_valid > d->Cout)) return DFGAN_E_ARG;
   if (d->phase_cout && (d->phase_cout % 16 || d->Cout != 4 * d->phase_cout || d->out_nchw)) return DFGAN_E_ARG;
   if (d->n_src < 1 || d->n_src > DFGAN_MAX_SRC || d->n_taps < 1 || d->n_taps > DFGAN_MAX_TAPS)
