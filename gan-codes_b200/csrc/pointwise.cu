@@ -30,6 +30,14 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf8& r) {
   u.w = pack_bf16x2(r.v[6], r.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// 16 consecutive channels of one pixel as ONE 256-bit store (a full 32-byte sector per instruction: kernels in which
+// every thread owns a whole pixel row would otherwise write each sector in two 16-byte halves)
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const float* v) {
+  uint4 lo, hi;
+  lo.x = pack_bf16x2(v[0], v[1]), lo.y = pack_bf16x2(v[2], v[3]), lo.z = pack_bf16x2(v[4], v[5]), lo.w = pack_bf16x2(v[6], v[7]);
+  hi.x = pack_bf16x2(v[8], v[9]), hi.y = pack_bf16x2(v[10], v[11]), hi.z = pack_bf16x2(v[12], v[13]), hi.w = pack_bf16x2(v[14], v[15]);
+  stg256(p, lo, hi);
+}
 __device__ __forceinline__ bf8 ldf8(const float* p) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -373,13 +381,8 @@ __global__ void __launch_bounds__(kPwThreads)
 #pragma unroll
   for (int i = 27; i < 32; ++i) v[i] = 0.f;
   __nv_bfloat16* dst = out + (static_cast<long long>(n) * H * W + p) * 32;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    bf8 t;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t.v[i] = v[q * 8 + i];
-    st8(dst + q * 8, t);
-  }
+  st16(dst, v);
+  st16(dst + 16, v + 16);
 }
 
 // Backward of tanh at the generator output (generator/model.py:29): g_t = g_img * (1 - img^2), packed as
@@ -399,13 +402,10 @@ __global__ void __launch_bounds__(kPwThreads)
       g[c] = __ldg(g_img + o) * (1.f - y * y);
     }
     __nv_bfloat16* dst = out + (static_cast<long long>(n) * HW + p) * 32;
-    bf8 t{};
-    t.v[0] = g[0], t.v[1] = g[1], t.v[2] = g[2];
-    st8(dst, t);
-    const bf8 z{};
-    st8(dst + 8, z);
-    st8(dst + 16, z);
-    st8(dst + 24, z);
+    float t[16] = {g[0], g[1], g[2], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    st16(dst, t);
+    const float z[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    st16(dst + 16, z);
   }
   if (dbias) {
     // the bias gradient uses the bf16-rounded values the weight-gradient GEMM will see
