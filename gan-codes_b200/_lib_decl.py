@@ -17,6 +17,8 @@ def declare(l: C.CDLL) -> None:
     l.dfgan_pack_entry_size.restype = C.c_int
     l.dfgan_pack_entry_bs_offset.argtypes = []
     l.dfgan_pack_entry_bs_offset.restype = C.c_int
+    l.dfgan_unpack_entry_size.argtypes = []
+    l.dfgan_unpack_entry_size.restype = C.c_int
     for name, argtypes in _TABLE.items():
         fn = getattr(l, name)   # AttributeError = header and library disagree: fail loudly
         fn.argtypes = argtypes
@@ -43,6 +45,8 @@ _TABLE: dict = {
     "dfgan_pack_entry_fill": [P, P, P, I, I, I, I, I, I, I, P, F, I, I],
     "dfgan_pack_batched": [P, I, I, P],
     "dfgan_unfold_subpixel_wgrad": [P, P, I, I, P],
+    "dfgan_unpack_entry_fill": [P, P, P, I, I, I, I],
+    "dfgan_wgrad_unpack": [P, I, I, P],
     "dfgan_sqnorm": [P, L, P, P],
     "dfgan_sqnorm_det": [P, L, P, P, I, P],
     "dfgan_adam_step": [P, P, P, P, L, P, P, F, F, F, F, F, F, P],
@@ -56,4 +60,5 @@ _TABLE: dict = {
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
            "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size", "dfgan_pack_entry_bs_offset", "dfgan_conv_uses_image",
+           "dfgan_unpack_entry_size",
            *_TABLE.keys()]

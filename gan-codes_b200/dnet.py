@@ -58,6 +58,14 @@ class DPacked:
         self.ch, self.ccat = wh.shape[0], wh.shape[1]
         self.wh_f, self.wh_d = e(9 * self.ch, self.ccat), e(9 * self.ccat, self.ch)
         self._ptrs = None
+        # tap-major scratch for the weight gradients of every 4x4 / 3x3 convolution (coalesced fp32 atomics),
+        # folded back into the OIHW gradients once per sweep (K.WgradScratch)
+        shapes = {}
+        for (p, _, _, _) in self.plan:
+            for nm in (p + ".residual_conv.0.weight", p + ".residual_conv.2.weight"):
+                shapes[nm] = tuple(params[nm].shape)
+        shapes["img_sentence_forward.0.weight"] = tuple(wh.shape)
+        self.ws = K.WgradScratch(shapes, dev)
         self.refresh(params)
 
     def _build(self, params: Dict[str, torch.Tensor]) -> None:
@@ -176,12 +184,12 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
             co.join(dev, co.POOL_PHASE)
         if grads is not None:
             # weight gradients leave the data-gradient chain: side stream, joined at the end of the sweep
-            w3, w4 = params[p + ".residual_conv.2.weight"], params[p + ".residual_conv.0.weight"]
             pv = co.parity_views(x)
+            n3, n4 = p + ".residual_conv.2.weight", p + ".residual_conv.0.weight"
             with co.side(n_side, dev):
-                co.wgrad_run([c1], TAPS3_ID, g_c2, grads[p + ".residual_conv.2.weight"], _oihw_strides(w3))
+                co.wgrad_run([c1], TAPS3_ID, g_c2, pk.ws.view(n3), pk.ws.strides(n3))
             with co.side(n_side + 1, dev):
-                co.wgrad_run(pv, TAPS4_ID, g_c1, grads[p + ".residual_conv.0.weight"], _oihw_strides(w4))
+                co.wgrad_run(pv, TAPS4_ID, g_c1, pk.ws.view(n4), pk.ws.strides(n4))
                 if sc:
                     ws = params[p + ".scale_conv.weight"]
                     co.wgrad_run(pv, TAPS_POOL, g_y, grads[p + ".scale_conv.weight"], _oihw_strides(ws),
@@ -201,6 +209,8 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
         gx = torch.empty(n, 3, hh, hh, device=dev, dtype=F32)
         co.conv_run([g_y], co.taps_3x3_dgrad(16), pk.w0_d, 16, None, out_nchw=gx, co_valid=3)
     co.join(dev)
+    if grads is not None:
+        pk.ws.flush(grads, [n for n in pk.ws.shapes if n.startswith("img_forward.")])
     return gx
 
 
@@ -235,13 +245,13 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
             if sc:
                 co.wgrad_run(pv, TAPS_POOL, c_y, grads[p + ".scale_conv.weight"],
                              _oihw_strides(params[p + ".scale_conv.weight"]), scale_imm=0.25)
-            co.wgrad_run(pv, TAPS4_ID, c_c1, grads[p + ".residual_conv.0.weight"],
-                         _oihw_strides(params[p + ".residual_conv.0.weight"]))
+            n4 = p + ".residual_conv.0.weight"
+            co.wgrad_run(pv, TAPS4_ID, c_c1, pk.ws.view(n4), pk.ws.strides(n4))
         t_c1 = e(n, h, w, cout)
         co.conv_run(pv, co.taps_4x4s2(cout), b["w4_f"], cout, t_c1, mask_src=c1)
         with co.side(n_side + 1, dev):
-            co.wgrad_run([t_c1], TAPS3_ID, c_c2, grads[p + ".residual_conv.2.weight"],
-                         _oihw_strides(params[p + ".residual_conv.2.weight"]))
+            n3 = p + ".residual_conv.2.weight"
+            co.wgrad_run([t_c1], TAPS3_ID, c_c2, pk.ws.view(n3), pk.ws.strides(n3))
         t_y, t_r = e(n, h, w, cout), e(n, h, w, cout)
         co.conv_run([t_c1], co.taps_3x3(cout), b["w3_f"], cout, t_y, mask_src=r, aux=t_r,
                     scale_dev=params[p + ".gamma"], addend=t_s)
@@ -250,6 +260,7 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
         n_side += 2
         t_x = t_y
     co.join(dev)
+    pk.ws.flush(grads, [n for n in pk.ws.shapes if n.startswith("img_forward.")])
     return t_x
 
 
@@ -286,8 +297,9 @@ def head_backward(pk: DPacked, params, ctx: dict, g_logit: Optional[torch.Tensor
     g_cat = torch.empty_like(cat)
     co.conv_run([g_hid], co.taps_3x3_dgrad(pk.ccat), pk.wh_d, pk.ccat, g_cat)
     if grads is not None:
-        co.wgrad_run([cat], TAPS3_ID, g_hid, grads["img_sentence_forward.0.weight"],
-                     _oihw_strides(params["img_sentence_forward.0.weight"]))
+        nh = "img_sentence_forward.0.weight"
+        co.wgrad_run([cat], TAPS3_ID, g_hid, pk.ws.view(nh), pk.ws.strides(nh))
+        pk.ws.flush(grads, [nh])
     ce = pk.ccat - SENT_DIM
     g_embed = torch.empty(b, ce, 4, 4, device=dev, dtype=F32)
     g_sent = torch.empty(b, SENT_DIM, device=dev, dtype=F32) if need_sent else None
@@ -307,8 +319,9 @@ def head_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_embed: torch.Tens
     K.head_cat(t_embed, t_sent, t_cat, sscale=sscale)
     t_hid = torch.empty_like(hid)
     co.conv_run([t_cat], co.taps_3x3(pk.ch), pk.wh_f, pk.ch, t_hid, mask_src=hid)
-    co.wgrad_run([t_cat], TAPS3_ID, cots["hid"], grads["img_sentence_forward.0.weight"],
-                 _oihw_strides(params["img_sentence_forward.0.weight"]))
+    nh = "img_sentence_forward.0.weight"
+    co.wgrad_run([t_cat], TAPS3_ID, cots["hid"], pk.ws.view(nh), pk.ws.strides(nh))
+    pk.ws.flush(grads, [nh])
     K.head_out_bwd(cots["logit"], None, t_hid, params["img_sentence_forward.2.weight"], None,
                    grads["img_sentence_forward.2.weight"])
     t_logit = torch.empty(b, device=dev, dtype=F32)

@@ -61,6 +61,12 @@ class GPacked:
         self.wo_f, self.wo_d = e(9 * 16, self.c_last), e(9 * self.c_last, 32)
         self.bo16 = torch.zeros(16, device=dev, dtype=F32)
         self._ptrs = None
+        # tap-major scratch for the 3x3 weight gradients that are accumulated straight into OIHW tensors (conv_2 of
+        # every block, conv_1 of the first block, conv_out); see K.WgradScratch
+        shapes = {p + ".conv_2.weight": tuple(params[p + ".conv_2.weight"].shape) for (p, _, _, _) in self.plan}
+        shapes[self.plan[0][0] + ".conv_1.weight"] = tuple(params[self.plan[0][0] + ".conv_1.weight"].shape)
+        shapes["conv_out.1.weight"] = tuple(params["conv_out.1.weight"].shape)
+        self.ws = K.WgradScratch(shapes, dev)
         self.refresh(params)
 
     def _build(self, params: Dict[str, torch.Tensor]) -> None:
@@ -253,7 +259,7 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
     # every tensor they read until then
     keep, n_side = [g_t], 1
     with co.side(0, dev):
-        co.wgrad_run([act], TAPS3_ID, g_t, grads["conv_out.1.weight"], _oihw_strides(params["conv_out.1.weight"]),
+        co.wgrad_run([act], TAPS3_ID, g_t, pk.ws.view("conv_out.1.weight"), pk.ws.strides("conv_out.1.weight"),
                      co_valid=3)
     g_z = e(*z.shape)
     co.conv_run([g_t], co.taps_3x3_dgrad(pk.c_last), pk.wo_d, pk.c_last, g_z, mask_src=z)
@@ -270,8 +276,8 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
         q = e(n, hh, hh, c2)
         co.conv_run([g_z], co.taps_3x3_dgrad(c2), b["w2_d"], c2, q)
         with co.side(n_side, dev):
-            co.wgrad_run([a34], TAPS3_ID, g_z, grads[p + ".conv_2.weight"],
-                         _oihw_strides(params[p + ".conv_2.weight"]), scale_dev=gamma)
+            co.wgrad_run([a34], TAPS3_ID, g_z, pk.ws.view(p + ".conv_2.weight"), pk.ws.strides(p + ".conv_2.weight"),
+                         scale_dev=gamma)
         # shortcut branch: 2x2 sum (backward of the nearest upsample) + per-channel sums of g_z
         cs = cs_all[cs_off:cs_off + c2]
         cs_off += c2
@@ -302,7 +308,7 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
         else:
             co.conv_run([g_h1], co.taps_3x3_dgrad(c1), b["w1_d"], c1, g_a12)
             with co.side(n_side + 1, dev):
-                co.wgrad_run([a12], TAPS3_ID, g_h1, grads[p + ".conv_1.weight"], _oihw_strides(w1))
+                co.wgrad_run([a12], TAPS3_ID, g_h1, pk.ws.view(p + ".conv_1.weight"), pk.ws.strides(p + ".conv_1.weight"))
         if sc:
             t = e(n, h, h, c1)
             co.conv_run([pooled], co.taps_1x1(), b["ws_d"], c1, t)
@@ -316,5 +322,6 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
         n_side += 3
         g_z = g_prev
     co.join(dev)
+    pk.ws.flush(grads)
     K.nhwc_to_nchw(g_z, mlp.g_x0f.view(n, pk.c0, 4, 4))
     mlp.backward()

@@ -267,6 +267,61 @@ def unfold_subpixel_wgrad(folded, dw):
     _call("dfgan_unfold_subpixel_wgrad", _p(folded), _p(dw), co, ci, _s())
 
 
+class WgradScratch:
+    """Tap-major fp32 scratch [KK][Co][Ci] for every k x k convolution weight of a network, the target of the
+    weight-gradient GEMMs (their fp32 atomics are coalesced only when ci is the fastest index), and the batched
+    fold-back into the reference's OIHW gradients: `flush(grads)` adds every scratch tensor into grads[name] and
+    zeroes the scratch again (one launch)."""
+
+    def __init__(self, shapes: dict, device):
+        self.shapes, self.off, total = dict(shapes), {}, 0
+        for name, (co, ci, kh, kw) in self.shapes.items():
+            self.off[name] = total
+            total += ((co * ci * kh * kw + 7) // 8) * 8
+        self.buf = torch.zeros(max(total, 8), device=device, dtype=F32)
+        self.device = device
+        self._tables: dict = {}
+        self.esize = _lib.lib().dfgan_unpack_entry_size()
+
+    def __contains__(self, name: str) -> bool:
+        return name in self.shapes
+
+    def view(self, name: str):
+        co, ci, kh, kw = self.shapes[name]
+        n = co * ci * kh * kw
+        return self.buf[self.off[name]:self.off[name] + n].view(kh * kw, co, ci)
+
+    def strides(self, name: str) -> tuple:
+        co, ci, _, _ = self.shapes[name]
+        return (ci, 1, co * ci)          # (s_co, s_ci, s_tap) of the [tap][co][ci] scratch
+
+    def flush(self, grads: dict, names=None) -> None:
+        names = tuple(n for n in (names if names is not None else self.shapes) if n in self.shapes)
+        if not names:
+            return
+        key = (names, tuple(grads[n].data_ptr() for n in names))
+        tab = self._tables.get(key)
+        if tab is None:
+            entries, blocks = [], 0
+            for n in names:
+                co, ci, kh, kw = self.shapes[n]
+                g = grads[n]
+                assert g.dtype == F32 and g.is_contiguous() and tuple(g.shape) == (co, ci, kh, kw)
+                buf = (C.c_uint8 * self.esize)()
+                nb = _lib.lib().dfgan_unpack_entry_fill(C.cast(buf, C.c_void_p), self.view(n).data_ptr(),
+                                                        g.data_ptr(), co, ci, kh * kw, blocks)
+                if nb < 0:
+                    _lib.check(nb, "dfgan_unpack_entry_fill")
+                entries.append(bytes(buf))
+                blocks += nb
+            raw = torch.frombuffer(bytearray(b"".join(entries)), dtype=torch.uint8).to(self.device)
+            tab = (raw, len(entries), blocks)
+            if len(self._tables) > 8:
+                self._tables.clear()
+            self._tables[key] = tab
+        _call("dfgan_wgrad_unpack", tab[0].data_ptr(), tab[1], tab[2], _s())
+
+
 def gblock_small_grads(cs, gamma, bias2, g_bias2, g_gamma, g_sbias=None):
     """conv_2.bias / scale_conv.bias / gate gradients of a generator block from the per-channel cotangent sums."""
     for t in (cs, gamma, bias2, g_bias2, g_gamma):

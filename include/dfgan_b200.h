@@ -213,6 +213,13 @@ int dfgan_pack_entry_fill(void* entry_out, const float* w, void* out, int Co, in
                           int image, int block_start);
 int dfgan_pack_batched(const void* entries_dev, int n_entries, int total_blocks, dfgan_stream_t st);
 /* dw[co][ci][3][3] += un-folded sub-pixel weight gradient folded[16][co][ci]. */
+/* Tap-major weight-gradient scratch -> OIHW gradient: dst[co][ci][t] += src[t][co][ci]; src = 0.  dfgan_wgrad_run
+ * accumulates with fp32 atomics, which are coalesced only when ci is the fastest index; all scratch tensors of a
+ * network are folded back in ONE launch over a device table of dfgan_unpack_entry_size()-byte entries. */
+int dfgan_unpack_entry_size(void);
+int dfgan_unpack_entry_fill(void* entry_out, float* src, float* dst, int Co, int Ci, int KK, int block_start);
+int dfgan_wgrad_unpack(const void* entries_dev, int n_entries, int total_blocks, dfgan_stream_t st);
+
 int dfgan_unfold_subpixel_wgrad(const float* folded, float* dw, int Co, int Ci, dfgan_stream_t st);
 
 /* *out += sum g^2 ; then clip (global L2 norm, max_norm) + Adam over a flat buffer.  step: device int (>= 1).
