@@ -1696,7 +1696,8 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     n_tile = d->Cout <= 256 ? d->Cout : 256;
     // (halving N doubles the A-tile traffic and halves the tensor-pipe efficiency of each MMA, so only do it
     // while fewer than half of the SMs would have work)
-    while (n_tile > 64 && n_tile % 32 == 0 && d->Cout % (n_tile / 2) == 0 &&
+    static const int n_tile_min = getenv("DFGAN_NTILE_MIN") ? atoi(getenv("DFGAN_NTILE_MIN")) : 64;
+    while (n_tile > n_tile_min && n_tile % 32 == 0 && d->Cout % (n_tile / 2) == 0 &&
            2 * m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
       n_tile /= 2;
   }
@@ -1851,7 +1852,8 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
     // exactly one wave of work items: every split ends in 128 x n_tile fp32 atomics, and the measured optimum
     // (tools/prof_wgrad.py) is items ~= #SMs for the wide layers; narrow layers (few row tiles) keep more
     // splits because their main loop, not the atomics, dominates
-    ks = base_items >= 8 ? num_sms() / base_items : (2 * num_sms() + base_items - 1) / base_items;
+    static const int waves = getenv("DFGAN_WGRAD_WAVES") ? atoi(getenv("DFGAN_WGRAD_WAVES")) : 1;
+    ks = base_items >= 8 ? waves * num_sms() / base_items : (2 * num_sms() + base_items - 1) / base_items;
     // keep at least 4 pixel tiles per split so the accumulate chain amortises the epilogue
     int max_ks = k.pix_tiles / 4;
     if (max_ks < 1) max_ks = 1;
