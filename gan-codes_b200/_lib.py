@@ -42,6 +42,7 @@ class ConvDesc(C.Structure):
         ("tab_ga", C.c_void_p), ("tab_ba", C.c_void_p), ("tab_gb", C.c_void_p), ("tab_bb", C.c_void_p),
         ("tab_stride", C.c_int64), ("out_nchw", C.c_void_p), ("co_valid", C.c_int32), ("tanh_out", C.c_int32),
         ("wpack_img", C.c_void_p), ("img_rows_per_slot", C.c_int32), ("phase_cout", C.c_int32),
+        ("workspace", C.c_void_p), ("ws_bytes", C.c_int64),
     ]
 
 
@@ -84,6 +85,8 @@ def _declare(l: C.CDLL) -> None:
     l.dfgan_conv_run.restype = C.c_int
     l.dfgan_conv_uses_image.argtypes = [C.POINTER(ConvDesc)]
     l.dfgan_conv_uses_image.restype = C.c_int
+    l.dfgan_conv_splitk_bytes.argtypes = [C.POINTER(ConvDesc)]
+    l.dfgan_conv_splitk_bytes.restype = C.c_int64
     l.dfgan_wgrad_run.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
     l.dfgan_wgrad_run.restype = C.c_int
     l.dfgan_profile_enable.argtypes = [C.c_int]

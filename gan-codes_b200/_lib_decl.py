@@ -60,5 +60,5 @@ _TABLE: dict = {
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
            "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size", "dfgan_pack_entry_bs_offset", "dfgan_conv_uses_image",
-           "dfgan_unpack_entry_size",
+           "dfgan_unpack_entry_size", "dfgan_conv_splitk_bytes",
            *_TABLE.keys()]

@@ -18,6 +18,8 @@ from . import _lib
 from ._lib import ConvDesc, Tap, View4, WgradDesc
 
 SLOPE = 0.2
+SPLITK_MAX_PIXELS = 128 * 74   # more 128-pixel tiles than half the SMs never split (see plan_generic)
+_SPLITK_WS: dict = {}           # (stream, device) -> zeroed fp32 scratch of the split-K launches on that stream
 
 # packed operand (data_ptr) -> (the same operand in the swizzled shared-memory image layout, rows per image slot);
 # registered by the packers for C_in % 64 == 0, C_in >= 128 and picked up by conv_run for the wide-layer halo kernel
@@ -217,6 +219,18 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
     if TRACK_USAGE:
         uses_img = img is not None and _lib.lib().dfgan_conv_uses_image(C.byref(d)) == 1
         USED.add(img[0].data_ptr() if uses_img else wpack.data_ptr())
+    if n * h * w <= SPLITK_MAX_PIXELS:
+        # low-resolution launch: offer a zeroed fp32 scratch so the C side can split the K loop over the idle SMs.
+        # One persistent scratch per stream (launches on a stream are serialised; the second pass of a split launch
+        # leaves the scratch zeroed again), allocated outside any stream capture by the eager warm-up iterations.
+        nbytes = _lib.lib().dfgan_conv_splitk_bytes(C.byref(d))
+        if nbytes > 0:
+            key = (_stream(), wpack.device.index)
+            ws = _SPLITK_WS.get(key)
+            if ws is None or ws.numel() * 4 < nbytes:
+                ws = torch.zeros(max(nbytes // 4, 1 << 20), device=wpack.device, dtype=torch.float32)
+                _SPLITK_WS[key] = ws
+            d.workspace, d.ws_bytes = ws.data_ptr(), nbytes
     _lib.check(_lib.lib().dfgan_conv_run(C.byref(d), _stream()), "dfgan_conv_run")
 
 

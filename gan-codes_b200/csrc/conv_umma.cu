@@ -57,6 +57,8 @@ struct ConvK {
   int phase_cout;   // > 0: columns are 4 output phases x phase_cout channels of a 2x-upsampled output grid
   int col_split;    // halo kernels: both epilogue warpgroups work on EVERY tile (alternate 16-column chunks)
                     // instead of alternating tiles -- for launches with only 1-2 tiles per CTA
+  int k_splits;     // generic kernel: > 1 = split-K, each CTA runs a slice of the (tap, chunk) loop and adds its fp32
+  float* ws;        // partial tile to ws[pixel][Cout]; conv_splitk_epilogue_kernel applies the fused epilogue afterwards
   int dbg;          // DFGAN_DBG bit mask (conv_halo_kernel only): 1 skip epilogue body, 2 skip MMAs, 4 skip TMA loads,
                     // 8 skip tcgen05.ld -- bottleneck isolation, results are garbage
 };
@@ -282,7 +284,10 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     // whole warp runs the loop (coordinates stay warp-uniform -> uniform registers), one elected lane issues
     const bool leader = elect_one();
     PipeState ps;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    // work item = (tile, k-split): split s runs the slice [it0, it1) of the flattened (tap, chunk) loop
+    for (int item = blockIdx.x; item < p.total_tiles * p.k_splits; item += gridDim.x) {
+      const int tile = item / p.k_splits, ks = item - tile * p.k_splits;
+      const int it0 = (k_iters * ks) / p.k_splits, it1 = (k_iters * (ks + 1)) / p.k_splits;
       const int nt = tile % p.n_tiles_n;
       int mt = tile / p.n_tiles_n;
       const int tw = mt % p.tiles_w;
@@ -290,21 +295,20 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const int th = mt % p.tiles_h;
       const int tn = mt / p.tiles_h;
       const int w0 = tw << p.lbw, h0 = th << p.lbh, n0 = tn * (128 >> (p.lbw + p.lbh));
-      for (int t = 0; t < p.n_taps; ++t) {
+      for (int it = it0; it < it1; ++it) {
+        const int t = it / p.n_chunks, c = it - t * p.n_chunks;
         const CUtensorMap* ma = &maps.a[p.tap_src[t]];
         const int wy = h0 + p.tap_dy[t], wx = w0 + p.tap_dx[t];
         const int brow = p.tap_wrow[t] + nt * p.n_tile;
-        for (int c = 0; c < p.n_chunks; ++c) {
-          wait_bounded(&empty[ps.stage], ps.phase ^ 1);
-          uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
-          if (leader) {
-            mbar_expect_tx(&full[ps.stage], stage_bytes);
-            tma_load_4d(sa, ma, &full[ps.stage], c * BK, wx, wy, n0);
-            tma_load_2d(sa + p.a_bytes, &maps.b, &full[ps.stage], c * BK, brow);
-          }
-          __syncwarp();
-          ps.advance(p.n_stages);
+        wait_bounded(&empty[ps.stage], ps.phase ^ 1);
+        uint8_t* sa = smem + static_cast<size_t>(ps.stage) * stage_bytes;
+        if (leader) {
+          mbar_expect_tx(&full[ps.stage], stage_bytes);
+          tma_load_4d(sa, ma, &full[ps.stage], c * BK, wx, wy, n0);
+          tma_load_2d(sa + p.a_bytes, &maps.b, &full[ps.stage], c * BK, brow);
         }
+        __syncwarp();
+        ps.advance(p.n_stages);
       }
     }
   } else if (warp == 1) {
@@ -313,14 +317,16 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     uint32_t aphase = 0;
     constexpr uint32_t swz = (BK == 64) ? SWZ_128B : SWZ_64B;
     constexpr uint32_t sbo = 8u * BK * 2u;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.total_tiles * p.k_splits; item += gridDim.x) {
+      const int ks = item % p.k_splits;
+      const int it0 = (k_iters * ks) / p.k_splits, it1 = (k_iters * (ks + 1)) / p.k_splits;
       wait_bounded(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.n_tile);
       // descriptors are computed warp-uniformly (uniform registers); only the tcgen05 instructions are
       // predicated on the elected lane -- see the note in conv_halo_kernel
       const bool leader = elect_one();
-      for (int it = 0; it < k_iters; ++it) {
+      for (int it = it0; it < it1; ++it) {
         wait_bounded(&full[ps.stage], ps.phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         const uint64_t bdesc = make_smem_desc(a_addr + p.a_bytes, 16, sbo, swz);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (it | k) != 0);
+          if (leader) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, ((it - it0) | k) != 0);
         }
         if (leader) umma_commit(&empty[ps.stage]);
         __syncwarp();
@@ -348,7 +354,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
     const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < p.total_tiles * p.k_splits; item += gridDim.x) {
+      const int tile = item / p.k_splits;
       const int nt = tile % p.n_tiles_n;
       int mt = tile / p.n_tiles_n;
       const int tw = mt % p.tiles_w;
@@ -362,6 +369,28 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
                                           (w >> p.add_shift) * p.add_sw)
                                        : 0;
+      if (p.k_splits > 1) {
+        // split-K: add this slice's partial sums to the fp32 workspace; the fused epilogue runs in a second pass
+        wait_bounded(&tfull[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+        float* wrow = p.ws + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.Cout + nt * p.n_tile;
+        for (int c = 0; c < p.n_tile; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          if (valid && nt * p.n_tile + c < p.Cout) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(wrow + c + i, v[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+        continue;
+      }
       EpiPre nxt{};
       epi_pre_issue(p, nxt, valid, nt * p.n_tile, 0, n, h, w, o_off, a_off);
       wait_bounded(&tfull[as], aphase);
@@ -395,6 +424,40 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Second pass of a split-K launch: one thread per (pixel, 16-column chunk) reads the summed fp32 tile from the
+// workspace (and zeroes it for the next launch) and applies the same fused epilogue as the single-pass kernels.
+__global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const __grid_constant__ ConvK p) {
+  const int chunks = p.Cout / 16;
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * chunks;
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % chunks);
+  const long long pix = i / chunks;
+  const int w = static_cast<int>(pix % p.W), h = static_cast<int>((pix / p.W) % p.H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(p.W) * p.H));
+  float* src = p.ws + pix * p.Cout + c * 16;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 f = __ldcg(reinterpret_cast<const float4*>(src) + j);
+    v[4 * j] = f.x, v[4 * j + 1] = f.y, v[4 * j + 2] = f.z, v[4 * j + 3] = f.w;
+    reinterpret_cast<float4*>(src)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+  const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+  const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh + (w >> p.add_shift) * p.add_sw) : 0;
+  EpiPre pre{};
+  epi_pre_issue(p, pre, true, c * 16, 0, n, h, w, o_off, a_off);
+  const int gcol = c * 16;
+  if (p.phase_cout) {
+    const int ph = gcol / p.phase_cout;
+    const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
+    epilogue_chunk(p, v, gcol - ph * p.phase_cout, n, h, w, oo, a_off, scale, pre);
+  } else {
+    epilogue_chunk(p, v, gcol, n, h, w, o_off, a_off, scale, pre);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1521,6 +1584,67 @@ static double launch_bytes(const dfgan_conv_desc* d) {
   return bytes;
 }
 
+// Generic-kernel tiling: brick geometry, N tile, tile count and the number of K splits an under-filled launch wants.
+struct GenericPlan {
+  int lbw, lbh, n_tile, tiles_w, tiles_h, tiles_n, n_tiles_n, total_tiles, k_iters, k_splits;
+};
+static bool plan_generic(const dfgan_conv_desc* d, GenericPlan& g) {
+  brick_geometry(d->W, d->H, g.lbw, g.lbh);
+  const int BW = 1 << g.lbw, BH = 1 << g.lbh, BN = 128 / (BW * BH);
+  int n_tile = d->n_tile_hint;
+  if (n_tile <= 0) {
+    // widest N tile that still gives every SM a tile: small grids (low resolutions) trade A-tile re-reads
+    // from L2 for occupancy of the 148 SMs
+    const long long m_tiles = static_cast<long long>((d->W + BW - 1) / BW) * ((d->H + BH - 1) / BH) *
+                              ((d->N + BN - 1) / BN);
+    n_tile = d->Cout <= 256 ? d->Cout : 256;
+    // (halving N doubles the A-tile traffic and halves the tensor-pipe efficiency of each MMA, so only do it
+    // while fewer than half of the SMs would have work)
+    static const int n_tile_min = getenv("DFGAN_NTILE_MIN") ? atoi(getenv("DFGAN_NTILE_MIN")) : 64;
+    while (n_tile > n_tile_min && n_tile % 32 == 0 && d->Cout % (n_tile / 2) == 0 &&
+           2 * m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
+      n_tile /= 2;
+  }
+  if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return false;
+  g.n_tile = n_tile;
+  g.tiles_w = (d->W + BW - 1) / BW;
+  g.tiles_h = (d->H + BH - 1) / BH;
+  g.tiles_n = (d->N + BN - 1) / BN;
+  g.n_tiles_n = (d->Cout + n_tile - 1) / n_tile;
+  g.total_tiles = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles_n;
+  const int BK = (d->Cin % 64 == 0) ? 64 : 32;
+  g.k_iters = d->n_taps * (d->Cin / BK);
+  // split-K: an under-filled launch (fewer tiles than half the SMs) with a long K loop is bound by the load
+  // bandwidth of the few SMs it runs on (~60 B/cycle each); slices of the (tap, chunk) loop spread it over all SMs
+  // Measured on the training iteration: 12.02 -> 11.98 ms (the second pass and the atomics eat most of the gain, and
+  // these launches already overlap with the weight gradients on side streams), so it is opt-in: DFGAN_SPLITK=1.
+  static const bool splitk_off = getenv("DFGAN_SPLITK") == nullptr || atoi(getenv("DFGAN_SPLITK")) == 0;
+  g.k_splits = 1;
+  if (!splitk_off && d->n_tile_hint == 0 && !d->out_nchw && 2 * g.total_tiles <= num_sms() && g.k_iters >= 16) {
+    int sp = num_sms() / g.total_tiles;
+    if (sp > g.k_iters / 8) sp = g.k_iters / 8;
+    if (sp > 16) sp = 16;
+    if (sp >= 2) g.k_splits = sp;
+  }
+  return true;
+}
+static bool takes_halo_path(const dfgan_conv_desc* d) {
+  dfgan_conv_desc ds = *d;   // plan_halo is order-independent in its accept / reject decision
+  HaloK hp{};
+  int smem = 0;
+  if (getenv("DFGAN_NO_HALO") == nullptr && d->n_tile_hint == 0 && plan_halo(&ds, hp, smem)) return true;
+  Halo2K h2{};
+  int nt2 = 0;
+  return getenv("DFGAN_NO_HALO2") == nullptr && d->n_tile_hint == 0 && plan_halo2(d, h2, nt2, smem);
+}
+extern "C" int64_t dfgan_conv_splitk_bytes(const dfgan_conv_desc* d) {
+  if (!d || d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1 || d->n_taps < 1) return 0;
+  if (takes_halo_path(d)) return 0;
+  GenericPlan g{};
+  if (!plan_generic(d, g) || g.k_splits < 2) return 0;
+  return static_cast<int64_t>(d->N) * d->H * d->W * d->Cout * 4;
+}
+
 // 1 when dfgan_conv_run would take the wide-layer halo kernel (reads wpack_img), 0 when it reads wpack.
 extern "C" int dfgan_conv_uses_image(const dfgan_conv_desc* d) {
   if (!d) return 0;
@@ -1685,29 +1809,20 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
 
   ConvK k{};
   ConvMaps maps{};
-  brick_geometry(d->W, d->H, k.lbw, k.lbh);
+  GenericPlan gp{};
+  if (!plan_generic(d, gp)) return DFGAN_E_SHAPE;
+  k.lbw = gp.lbw, k.lbh = gp.lbh;
   const int BW = 1 << k.lbw, BH = 1 << k.lbh, BN = 128 / (BW * BH);
-  int n_tile = d->n_tile_hint;
-  if (n_tile <= 0) {
-    // widest N tile that still gives every SM a tile: small grids (low resolutions) trade A-tile re-reads
-    // from L2 for occupancy of the 148 SMs
-    const long long m_tiles = static_cast<long long>((d->W + BW - 1) / BW) * ((d->H + BH - 1) / BH) *
-                              ((d->N + BN - 1) / BN);
-    n_tile = d->Cout <= 256 ? d->Cout : 256;
-    // (halving N doubles the A-tile traffic and halves the tensor-pipe efficiency of each MMA, so only do it
-    // while fewer than half of the SMs would have work)
-    static const int n_tile_min = getenv("DFGAN_NTILE_MIN") ? atoi(getenv("DFGAN_NTILE_MIN")) : 64;
-    while (n_tile > n_tile_min && n_tile % 32 == 0 && d->Cout % (n_tile / 2) == 0 &&
-           2 * m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
-      n_tile /= 2;
-  }
-  if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return DFGAN_E_SHAPE;
-  k.tiles_w = (d->W + BW - 1) / BW;
-  k.tiles_h = (d->H + BH - 1) / BH;
-  k.tiles_n = (d->N + BN - 1) / BN;
-  k.n_tiles_n = (d->Cout + n_tile - 1) / n_tile;
-  k.total_tiles = k.tiles_w * k.tiles_h * k.tiles_n * k.n_tiles_n;
+  const int n_tile = gp.n_tile;
+  k.tiles_w = gp.tiles_w, k.tiles_h = gp.tiles_h, k.tiles_n = gp.tiles_n;
+  k.n_tiles_n = gp.n_tiles_n, k.total_tiles = gp.total_tiles;
   k.n_tile = n_tile;
+  k.k_splits = 1;
+  if (gp.k_splits > 1 && d->workspace &&
+      d->ws_bytes >= static_cast<int64_t>(d->N) * d->H * d->W * d->Cout * 4) {
+    k.k_splits = gp.k_splits;
+    k.ws = static_cast<float*>(d->workspace);
+  }
   k.N = d->N, k.H = d->H, k.W = d->W, k.Cout = d->Cout;
   k.n_taps = d->n_taps;
   k.n_chunks = d->Cin / BK;
@@ -1738,7 +1853,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   if (rc) return rc;
 
   const size_t smem = static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 1024 + 256;
-  int grid = k.total_tiles;
+  int grid = k.total_tiles * k.k_splits;
   const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
   if (grid > cap) grid = cap;
   const double pix = static_cast<double>(d->N) * d->H * d->W;
@@ -1759,6 +1874,11 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   count_launch();
+  if (k.k_splits > 1) {
+    const long long total = static_cast<long long>(d->N) * d->H * d->W * (d->Cout / 16);
+    conv_splitk_epilogue_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(k);
+    count_launch();
+  }
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;
 }

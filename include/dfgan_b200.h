@@ -101,12 +101,18 @@ typedef struct dfgan_conv_desc {
   int32_t img_rows_per_slot;  /* rows_pad the image was packed with (rows between consecutive 64-column chunks) */
   int32_t phase_cout; /* > 0: Cout == 4*phase_cout; column block p=(a,c) is written to pixel (2h+a, 2w+c) of the
                          outputs (merged sub-pixel phases), bias / tables / addend are indexed by co % phase_cout */
+  void* workspace;    /* optional ZEROED fp32 scratch of dfgan_conv_splitk_bytes(d) bytes: lets an under-filled
+                         launch (low resolutions: fewer than #SMs/2 tiles, long K loop) split the (tap, chunk) loop
+                         over several CTAs per tile; a second pass applies the epilogue and re-zeroes the scratch */
+  int64_t ws_bytes;
 } dfgan_conv_desc;
 
 int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream);
 /* 1 when dfgan_conv_run(d) reads d->wpack_img (wide-layer halo kernel), 0 when it reads d->wpack: lets a caller
  * that re-packs weights every optimiser step skip the operand copy it never uses. */
 int dfgan_conv_uses_image(const dfgan_conv_desc* d);
+/* bytes of zeroed workspace with which dfgan_conv_run(d) would run split-K (0: the launch does not split) */
+int64_t dfgan_conv_splitk_bytes(const dfgan_conv_desc* d);
 
 /*
  * dfgan_wgrad_run -- weight gradient of the same tap-list convolution (split-K over pixels, fp32 atomics):
