@@ -28,6 +28,28 @@ def test_network(name):
     assert bringup_nets.CASES[name](), name
 
 
+@pytest.mark.parametrize("name", ["fprop3_b", "fprop4s2", "dgrad", "epilogue", "subpixel"])
+def test_kernel_with_split_k(name):
+    """The opt-in split-K path of the generic conv kernel (DFGAN_SPLITK=1 is read once per process, hence the
+    subprocess): the low-resolution shapes of these cases split their K loop and run the second epilogue pass."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bringup_conv.py"), name],
+                       env=dict(os.environ, DFGAN_SPLITK="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["dfwd", "gfwd", "engine"])
+def test_network_with_split_k(name):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bringup_nets.py"), name],
+                       env=dict(os.environ, DFGAN_SPLITK="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_extension_is_loaded_and_counts_launches():
     from gan_codes_b200 import _lib
     n0 = _lib.launch_count()
