@@ -169,11 +169,11 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
       float b[16];
       load_f32x16(p.bias + col, b);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += b[i];
+      for (int i = 0; i < 16; i += 2) add2(v[i], v[i + 1], v[i], v[i + 1], b[i], b[i + 1]);
     }
     if (p.lrelu_pre) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+      for (int i = 0; i < 16; i += 2) lrelu2(v[i], v[i + 1], p.slope);
     }
     if (p.mask_src) {
       float m[16];
@@ -187,12 +187,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
       store_round_bf16x16(p.aux + o_off + col, v);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= scale;
+    for (int i = 0; i < 16; i += 2) mul2(v[i], v[i + 1], v[i], v[i + 1], scale, scale);
     if (p.addend) {
       float a[16];
       unpack_bf16x16(pre.a0, pre.a1, a);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += p.add_scale * a[i];
+      for (int i = 0; i < 16; i += 2) fma2(v[i], v[i + 1], a[i], a[i + 1], p.add_scale, p.add_scale, v[i], v[i + 1]);
     }
     if (p.out_nchw) {
       // image boundary: fp32 planar store, lanes of a warp hold consecutive w -> coalesced
@@ -221,14 +221,17 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
         load_f32x16_a32(p.tab_ga + t_off, ga);
         load_f32x16_a32(p.tab_ba + t_off, ba);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = lrelu(fmaf(ga[i], v[i], ba[i]), p.slope);
+        for (int i = 0; i < 16; i += 2) {
+          fma2(v[i], v[i + 1], ga[i], ga[i + 1], v[i], v[i + 1], ba[i], ba[i + 1]);
+          lrelu2(v[i], v[i + 1], p.slope);
+        }
         load_f32x16_a32(p.tab_gb + t_off, ga);
         load_f32x16_a32(p.tab_bb + t_off, ba);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf(ga[i], v[i], ba[i]);
+        for (int i = 0; i < 16; i += 2) fma2(v[i], v[i + 1], ga[i], ga[i + 1], v[i], v[i + 1], ba[i], ba[i + 1]);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+      for (int i = 0; i < 16; i += 2) lrelu2(v[i], v[i + 1], p.slope);
       store_bf16x16(p.out2 + o_off + col, v);
     }
 }

@@ -199,8 +199,40 @@ __device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi
                : "memory");
 }
 
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE round-to-nearest operations per instruction, results
+// bit-identical to the scalar forms).  The conv epilogues are instruction-issue bound, so halving the FMA count pays.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+// (x0, x1) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a0, a1)), "l"(f2_pack(b0, b1)), "l"(f2_pack(c0, c1)));
+  f2_unpack(d, x0, x1);
+}
+__device__ __forceinline__ void mul2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a0, a1)), "l"(f2_pack(b0, b1)));
+  f2_unpack(d, x0, x1);
+}
+__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a0, a1)), "l"(f2_pack(b0, b1)));
+  f2_unpack(d, x0, x1);
+}
+
 // 0 <= slope <= 1: max(v, slope * v) is the LeakyReLU (two instructions instead of compare + multiply + select)
 __device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, v * slope); }
+__device__ __forceinline__ void lrelu2(float& v0, float& v1, float slope) {
+  float s0, s1;
+  mul2(s0, s1, v0, v1, slope, slope);
+  v0 = fmaxf(v0, s0), v1 = fmaxf(v1, s1);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
