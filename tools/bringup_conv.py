@@ -561,6 +561,33 @@ def wgrad():
 
 
 @case
+def unpack():
+    """K.WgradScratch: tap-major scratch -> OIHW gradients (dfgan_wgrad_unpack), ragged shapes, accumulate + re-zero."""
+    torch = _setup()
+    from gan_codes_b200 import kernels as K
+    shapes = {"a": (3, 32, 3, 3), "b": (64, 768, 3, 3), "c": (40, 24, 4, 4), "d": (512, 256, 3, 3), "e": (33, 65, 1, 1)}
+    ws = K.WgradScratch(shapes, torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ok = True
+    for rnd in range(2):
+        grads = {n: torch.randn(*sh, device="cuda", generator=g) for n, sh in shapes.items()}
+        want = {}
+        for n, sh in shapes.items():
+            v = ws.view(n)
+            assert float(v.abs().max()) == 0.0, "scratch must be zero before a sweep"
+            v.copy_(torch.randn(v.shape, device="cuda", generator=g))
+            want[n] = grads[n] + v.permute(1, 2, 0).reshape(sh)      # [KK][Co][Ci] -> [Co][Ci][KK]
+        ws.flush(grads)
+        torch.cuda.synchronize()
+        for n in shapes:
+            err = float((grads[n] - want[n]).abs().max())
+            zero = float(ws.view(n).abs().max())
+            print(f"unpack round {rnd} {n} {shapes[n]}: max err {err:.2e}, scratch after flush {zero:.1e}")
+            ok &= err == 0.0 and zero == 0.0
+    return ok
+
+
+@case
 def perf():
     torch = _setup()
     from gan_codes_b200 import convops as co
