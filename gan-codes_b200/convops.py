@@ -10,6 +10,7 @@ convs), discriminator/residual_block.py:11,13,19 (4x4 stride-2, 3x3, 1x1), discr
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
 from typing import Optional, Sequence
 
 import torch
@@ -36,8 +37,6 @@ TRACK_USAGE = False
 # current stream with events, so under stream capture they become parallel branches of the CUDA graph and fill the
 # SMs a small-grid kernel leaves idle.  SIDE_ENABLED = False serialises everything on the current stream (used by
 # the per-kernel timing pass of bench.py and by DFGAN_NO_SIDE=1).
-import os as _os
-
 SIDE_ENABLED = _os.environ.get("DFGAN_NO_SIDE", "0") != "1"
 N_SIDE = 3            # streams per pool
 POOL_PHASE, POOL_WGRAD = 0, 1
