@@ -82,8 +82,10 @@ class side:
 
 def join(dev, pool: int = POOL_WGRAD) -> None:
     """The current stream waits for every side stream of the pool that received work since its last join."""
+    if not SIDE_ENABLED:
+        return
     key = _dev_key(dev)
-    if not SIDE_ENABLED or key not in _SIDE_STREAMS:
+    if key not in _SIDE_STREAMS:
         return
     cur = torch.cuda.current_stream(dev)
     for i, s in enumerate(_SIDE_STREAMS[key][pool]):

@@ -86,3 +86,34 @@ def test_tap_tables():
         covered = sorted(t for s in slots[ph * 4:(ph + 1) * 4] for t in s)
         assert covered == list(range(9))
     assert len(convops.taps_subpixel_dgrad(64)) == 16
+
+
+def test_precision_tier_switch_and_no_cpu_path():
+    """set_precision selects the bf16 fast path or the fp32 verification tier; neither has a CPU path, and the
+    fp32 tier keeps the reference's state_dict layout (it runs on the same parameter containers)."""
+    G, D = Generator(32, 100), Discriminator(32)
+    keys_g, keys_d = list(G.state_dict()), list(D.state_dict())
+    assert G.set_precision("fp32") is G and D.set_precision("fp32") is D
+    assert list(G.state_dict()) == keys_g and list(D.state_dict()) == keys_d
+    with pytest.raises(ValueError):
+        G.set_precision("fp16")
+    for prec in ("fp32", "bf16"):
+        G.set_precision(prec), D.set_precision(prec)
+        with pytest.raises(RuntimeError):
+            G(torch.randn(2, 100), torch.randn(2, 256))
+        with pytest.raises(RuntimeError):
+            D.build_embeds(torch.randn(2, 3, 256, 256))
+        with pytest.raises(RuntimeError):
+            D.get_logits(torch.randn(2, 512, 4, 4), torch.randn(2, 256))
+
+
+def test_side_stream_helpers_are_inert_without_cuda_work():
+    """convops.side / join are pure scheduling helpers: disabled they must not touch any CUDA state."""
+    was = convops.SIDE_ENABLED
+    convops.SIDE_ENABLED = False
+    try:
+        with convops.side(0, torch.device("cpu")):
+            pass
+        convops.join(torch.device("cpu"))
+    finally:
+        convops.SIDE_ENABLED = was
