@@ -4,6 +4,8 @@
 // All activations are contiguous NHWC bf16 [N][HW][C] with C % 8 == 0; every thread moves 16-byte vectors
 // (8 channels), a warp covers consecutive channels/pixels so global accesses are fully coalesced.
 #include "host_common.h"
+
+#include <cstdlib>
 #include "sm100_ptx.cuh"
 
 namespace dfgan {
@@ -535,12 +537,16 @@ static inline int blocks_for(long long total, int threads) {
 }
 static inline bool c_ok(int C) { return C >= 8 && C % 8 == 0 && (kPwThreads % (C / 8)) == 0; }
 static inline bool c4_ok(int C) { return C >= 4 && C % 4 == 0 && C / 4 <= kPwThreads && (kPwThreads % (C / 4)) == 0; }
-// pixels per block so that the grid has roughly 8 blocks per SM (two waves at occupancy 4); measured better than
-// one fat wave for the backward kernels (tools/prof_pointwise.py)
-static inline int pick_ppb(int N, int HW, int C) {
+// Pixels per block such that the grid is an exact number of resident waves: `bps` blocks per SM, rounded DOWN per
+// image -- a grid that spills a few blocks into an extra wave costs a whole extra pass (measured with
+// tools/prof_pointwise.py: pool 46 -> 36 us and 49 -> 27 us, dres_bwd 74 -> 58 us at 32x128x128x64 once the grid fits).
+// Per kernel: bps = its occupancy (one wave of fat blocks) or twice that; DFGAN_PW_BPS overrides for experiments.
+static inline int pick_ppb(int N, int HW, int C, int bps) {
   const int ppi = kPwThreads / (C / 8);
-  long long want_blocks = 8LL * num_sms();
-  long long per_n = (want_blocks + N - 1) / N;
+  static const int bps_env = getenv("DFGAN_PW_BPS") ? atoi(getenv("DFGAN_PW_BPS")) : 0;
+  long long want_blocks = static_cast<long long>(bps_env > 0 ? bps_env : bps) * num_sms();
+  long long per_n = want_blocks / N;   // floor: the grid must not spill a few blocks into an extra wave
+  if (per_n < 1) per_n = 1;
   int ppb = static_cast<int>((HW + per_n - 1) / per_n);
   ppb = ((ppb + ppi - 1) / ppi) * ppi;
   if (ppb < ppi * 4) ppb = ppi * 4;
@@ -639,7 +645,7 @@ int dfgan_affine2_bwd(const void* g_a, const void* x, const void* g_add, void* g
                       float* colsum, int N, int HW, int C, dfgan_stream_t st) {
   if (!g_a || !x || !gx || !ga || !ba || !gb || !bb || !d_ga || !d_ba || !d_gb || !d_bb || !c4_ok(C))
     return DFGAN_E_ARG;
-  const int ppb = pick_ppb(N, HW, 2 * C);   // C/4 threads per pixel -> 1024/C pixels per iteration
+  const int ppb = pick_ppb(N, HW, 2 * C, 6);   // C/4 threads per pixel -> 1024/C pixels per iteration; occupancy 3
   affine2_bwd_kernel<<<dim3((HW + ppb - 1) / ppb, N), kPwThreads, 0, STREAM(st)>>>(
       static_cast<const __nv_bfloat16*>(g_a), static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(g_add), static_cast<__nv_bfloat16*>(gx), ga, ba, gb, bb, d_ga, d_ba,
@@ -652,7 +658,7 @@ int dfgan_affine2_bwd(const void* g_a, const void* x, const void* g_add, void* g
 int dfgan_pool(const void* x, void* out, float* colsum, const float* cs_dev, float cs_imm, int N, int Ho,
                int Wo, int C, int shift, float scale, dfgan_stream_t st) {
   if (!x || (!out && !colsum) || !c_ok(C) || shift < 0 || shift > 1) return DFGAN_E_ARG;
-  const int ppb = pick_ppb(N, Ho * Wo, C);
+  const int ppb = pick_ppb(N, Ho * Wo, C, 3);
   const dim3 grid((Ho * Wo + ppb - 1) / ppb, N);
   if (shift)
     pool_kernel<1, 1><<<grid, kPwThreads, 0, STREAM(st)>>>(static_cast<const __nv_bfloat16*>(x),
@@ -670,7 +676,7 @@ int dfgan_pool(const void* x, void* out, float* colsum, const float* cs_dev, flo
 int dfgan_dres_bwd(const void* g_y, const void* r, void* g_pre, const float* gamma, float* dgamma,
                    float* colsum, int N, int HW, int C, dfgan_stream_t st) {
   if (!g_y || !r || !g_pre || !gamma || !c_ok(C)) return DFGAN_E_ARG;
-  const int ppb = pick_ppb(N, HW, C);
+  const int ppb = pick_ppb(N, HW, C, 4);
   dres_bwd_kernel<<<dim3((HW + ppb - 1) / ppb, N), kPwThreads, 0, STREAM(st)>>>(
       static_cast<const __nv_bfloat16*>(g_y), static_cast<const __nv_bfloat16*>(r),
       static_cast<__nv_bfloat16*>(g_pre), gamma, dgamma, colsum, HW, C, ppb, 0.2f);
