@@ -21,6 +21,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
+from . import checkpoint as ckpt
 from . import convops as co
 from . import dnet, gnet
 from . import kernels as K
@@ -35,23 +36,20 @@ class FlatState:
     def __init__(self, module: nn.Module, lr: float, betas=(0.0, 0.9), eps: float = 1e-8, clip: float = 5.0):
         named = list(module.named_parameters())
         dev = named[0][1].device
-        sizes = [((p.numel() + 3) // 4) * 4 for _, p in named]
-        total = sum(sizes)
+        self.layout, total = ckpt.build_layout([(n, p.shape) for n, p in named])
         self.flat = torch.zeros(total, device=dev, dtype=F32)
         self.grad = torch.zeros(total, device=dev, dtype=F32)
         self.m = torch.zeros(total, device=dev, dtype=F32)
         self.v = torch.zeros(total, device=dev, dtype=F32)
         self.params: Dict[str, torch.Tensor] = {}
         self.grads: Dict[str, torch.Tensor] = {}
-        o = 0
         with torch.no_grad():
-            for (n, p), s in zip(named, sizes):
+            for (n, p), (_, o, _shape) in zip(named, self.layout):
                 view = self.flat[o:o + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
                 self.params[n] = view
                 self.grads[n] = self.grad[o:o + p.numel()].view(p.shape)
-                o += s
         self.n_real = sum(p.numel() for _, p in named)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
         self.sumsq = torch.zeros(1, device=dev, dtype=F32)
@@ -80,6 +78,23 @@ class FlatState:
         self.reduce(world)
         self.apply(world)
 
+    # torch.optim.Adam-compatible state (deep_fusion_gan/model.py:118-119, 305-306); reads the device step
+    # counter, i.e. synchronises -- checkpoint time only, never inside an iteration
+    def state_dict(self) -> dict:
+        return ckpt.adam_state_dict(self.layout, self.m, self.v, int(self.step_count.item()), self.lr, self.betas,
+                                    self.eps)
+
+    def load_state_dict(self, sd: dict) -> None:
+        with torch.no_grad():
+            h = ckpt.load_adam_state_dict(sd, self.layout, self.m, self.v)
+            self.step_count.fill_(h["step"])
+        if (h["betas"], h["eps"]) != (tuple(self.betas), self.eps) or h["lr"] != self.lr:
+            # hyper-parameters are launch arguments baked into a captured graph: adopt them only before capture
+            if getattr(self, "frozen", False):
+                raise RuntimeError("checkpoint Adam hyper-parameters differ from the ones captured in the CUDA "
+                                   f"graph (lr {h['lr']} betas {h['betas']} eps {h['eps']})")
+            self.lr, self.betas, self.eps = h["lr"], h["betas"], h["eps"]
+
 
 class DFGANTrainer:
     """step(images, sentence_embeds, noise) == one iteration of the reference's training loop."""
@@ -93,6 +108,9 @@ class DFGANTrainer:
         self.batch, self.world = batch, world
         self.gs = FlatState(generator, lr_g, betas, clip=clip)
         self.ds = FlatState(discriminator, lr_d, betas, clip=clip)
+        # the reference trainer's attribute names (deep_fusion_gan/model.py:28-29, 42-43)
+        self.generator, self.discriminator = generator, discriminator
+        self.g_optim, self.d_optim = self.gs, self.ds
         with torch.no_grad():
             self.gpk = gnet.GPacked(self.gs.params)
             self.dpk = dnet.DPacked(self.ds.params)
@@ -230,6 +248,7 @@ class DFGANTrainer:
                 self._graphs.append((g, st))
         self._graph = self._graphs[0][0]
         self._graph_out = self._seg_out
+        self.gs.frozen = self.ds.frozen = True
 
     @torch.no_grad()
     def step(self, images: torch.Tensor, sentence_embeds: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -304,3 +323,37 @@ class DFGANTrainer:
         mlp = self.mlp if n == self.batch else gnet.GMlp(self.gs.params, self.gpk.plan, n, None)
         return gnet.generator_forward(self.gpk, self.gs.params, mlp, noise.to(dev, F32).contiguous(),
                                       sentence_embeds.to(dev, F32).contiguous(), None)
+
+    # ------------------------------------------------------------------------------------ checkpoints
+    def checkpoint(self, epoch: int, **histories) -> dict:
+        """The reference's checkpoint dictionary (deep_fusion_gan/model.py:300-312) for the current state;
+        histories: g_losses, d_losses, d_gp_losses, is_scores, fid_scores, txtimg_losses (lists)."""
+        torch.cuda.synchronize(self.gs.flat.device)
+        # parameters are views of the flat buffer: clone, so the file holds one compact storage per tensor (like the
+        # reference's) and the dictionary does not change under the caller when training continues
+        own = lambda sd: type(sd)((k, v.detach().clone()) for k, v in sd.items())  # noqa: E731
+        return ckpt.make_checkpoint(epoch, own(self.G.state_dict()), own(self.D.state_dict()),
+                                    self.gs.state_dict(), self.ds.state_dict(), histories)
+
+    def save_checkpoint(self, save_dir: str, epoch: int, **histories):
+        """_save_checkpoint + _save_gen_weights (:298-327): `checkpoint.pt`, every tenth epoch
+        `checkpoint_epoch_{e}.pt`, and `gen_{e}.pth`.  Returns the paths written."""
+        return ckpt.write_checkpoint(self.checkpoint(epoch, **histories), save_dir)
+
+    def load_from_checkpoint(self, checkpoint_path: str):
+        """load_from_checkpoint (:106-133): restores both networks and both optimisers from a checkpoint written
+        by this trainer or by the reference's, re-packs the tensor-core operand copies of the weights, and returns
+        (epoch, g_losses, d_losses, d_gp_losses, is_scores, fid_scores, txtimg_losses)."""
+        dev = self.gs.flat.device
+        ck = ckpt.read_checkpoint(checkpoint_path, map_location=dev)
+        torch.cuda.synchronize(dev)
+        # parameters are views of the flat buffers, so load_state_dict's in-place copies fill them
+        self.G.load_state_dict(ck["generator"])
+        self.D.load_state_dict(ck["discriminator"])
+        self.gs.load_state_dict(ck["g_optimizer"])
+        self.ds.load_state_dict(ck["d_optimizer"])
+        with torch.no_grad():
+            self.gpk.refresh(self.gs.params)
+            self.dpk.refresh(self.ds.params)
+        self.g_ctx = {}
+        return (ck["epoch"],) + ckpt.histories_of(ck)

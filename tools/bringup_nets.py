@@ -353,6 +353,75 @@ def graph_side_consistency():
 
 
 @case
+def checkpoint():
+    """Reference-format checkpoints (deep_fusion_gan/model.py:106-133, 298-327) through the trainer: trainer A runs
+    four iterations (the last two as graph replays) and saves; trainer B -- fresh default-initialised networks that
+    have already taken a step of their own -- loads the file.  B's parameters, Adam moments and step counters then
+    equal A's bit for bit, its re-packed tensor-core operands produce bit-identical samples, the next iteration
+    of both agrees up to atomic-order noise, A itself resumes from the file after its graph was captured, and
+    torch.optim.Adam accepts the optimiser dictionaries."""
+    import os
+    import tempfile
+    torch, O, g_sd, d_sd, images, sent, noise = _states(batch=4, ws=1.0)
+    from gan_codes_b200.engine import DFGANTrainer
+    from gan_codes_b200.modules import Discriminator, Generator
+    G, D = _ref_modules(torch, O, g_sd, d_sd)
+    a = DFGANTrainer(G, D, 4, use_graph=True)
+    for _ in range(4):
+        a.step(images, sent, noise)
+    assert a._graph is not None
+    hist = dict(g_losses=[0.5], d_losses=[1.9], d_gp_losses=[0.1], is_scores=[1.5], fid_scores=[300.0],
+                txtimg_losses=[3.0])
+    G2, D2 = Generator(32, 100).cuda(), Discriminator(32).cuda()
+    b = DFGANTrainer(G2, D2, 4, use_graph=False)
+    b.step(images, sent, noise)
+    ok = True
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = a.save_checkpoint(tmp, 9, **hist)
+        ok &= sorted(os.path.basename(p) for p in paths) == ["checkpoint.pt", "checkpoint_epoch_9.pt", "gen_9.pth"]
+        ret = b.load_from_checkpoint(os.path.join(tmp, "checkpoint.pt"))
+        ok &= ret[0] == 9 and list(ret[1:]) == [hist[k] for k in ("g_losses", "d_losses", "d_gp_losses", "is_scores",
+                                                                 "fid_scores", "txtimg_losses")]
+        exact = all(torch.equal(x, y) for sa, sb in ((a.gs, b.gs), (a.ds, b.ds))
+                    for x, y in ((sa.flat, sb.flat), (sa.m, sb.m), (sa.v, sb.v), (sa.step_count, sb.step_count)))
+        print("  restored parameters / moments / step counters bit-identical:", exact,
+              "| steps G", int(b.gs.step_count), "D", int(b.ds.step_count))
+        ok &= exact and int(b.gs.step_count) == 4 and int(b.ds.step_count) == 8
+        rows = [("sample() after load vs source trainer", rel(b.sample(noise, sent), a.sample(noise, sent)))]
+        ok &= _report(rows, 1e-6)
+
+        # torch.optim.Adam takes the optimiser dictionaries (what the reference's load_from_checkpoint does, :118-119)
+        ck = torch.load(os.path.join(tmp, "checkpoint.pt"), weights_only=False)
+        for net, st, key in ((G2, b.gs, "g_optimizer"), (D2, b.ds, "d_optimizer")):
+            opt = torch.optim.Adam(net.parameters(), lr=1.0)
+            opt.load_state_dict(ck[key])
+            same = all(torch.equal(opt.state[p]["exp_avg_sq"], st.v[o:o + p.numel()].view(p.shape))
+                       for p, (_, o, _) in zip(net.parameters(), st.layout))
+            print(f"  torch.optim.Adam.load_state_dict({key}): lr {opt.param_groups[0]['lr']}, moments equal: {same}")
+            ok &= same and opt.param_groups[0]["lr"] == st.lr
+        ok &= list(torch.load(os.path.join(tmp, "gen_9.pth"))) == list(G.state_dict())
+
+        # the next iteration from the restored state: A as a graph replay, B as eager launches
+        def run(tr):
+            out = tr.step(images, sent, noise)
+            torch.cuda.synchronize()
+            return [out[k].item() for k in ("d_loss", "gp_loss", "g_loss")], tr.ds.flat.clone(), tr.gs.flat.clone()
+        la, da, ga = run(a)
+        lb, db, gb = run(b)
+        # ... and A resumes from the file after capture: the replay reads the restored buffers
+        a.load_from_checkpoint(os.path.join(tmp, "checkpoint.pt"))
+        lc, dc, gc = run(a)
+    print("  next-iteration losses: source", la, "| loaded", lb, "| source reloaded", lc)
+    rows = [("D parameters after the next iteration (loaded)", rel(db, da)), ("G parameters (loaded)", rel(gb, ga)),
+            ("D parameters (source reloaded)", rel(dc, da)), ("G parameters (source reloaded)", rel(gc, ga))]
+    for name, l in (("loaded", lb), ("reloaded", lc)):
+        for i, (x, y) in enumerate(zip(l, la)):
+            rows.append((f"loss {i} ({name})" + (" / 4" if i == 1 else ""),
+                         abs(x - y) / (abs(y) + 1e-6) / (4 if i == 1 else 1)))
+    return ok & _report(rows, 2e-2)
+
+
+@case
 def fp32_kernels():
     """dfgan_conv2d_f32_{fprop,dgrad,wgrad} (through gan_codes_b200.fp32.conv2d and torch autograd, first and
     second order) vs torch fp64 for every convolution geometry of the two networks (+ ragged sizes)."""
