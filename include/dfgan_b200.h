@@ -269,6 +269,24 @@ int dfgan_conv2d_f32_dgrad(const float* gy, const float* w, float* gx, int N, in
 int dfgan_conv2d_f32_wgrad(const float* x, const float* gy, float* gw, int N, int Cin, int H, int W, int Cout, int KH,
                            int KW, int stride, int pad, int OH, int OW, dfgan_stream_t st);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Frozen text encoder: RNNEncoder.forward (text_encoder/model.py:33-56) in eval mode -- nn.Embedding lookup,
+ * one bidirectional nn.LSTM layer over the length-packed batch (pack_padded_sequence, :39-44), sentence embedding
+ * = [final h of the forward direction | final h of the reverse direction] (:54-56).  Called once per training
+ * iteration (deep_fusion_gan/model.py:171) and again inside damsm/loss.py:14.
+ *   tokens [B,T] int64 (padded captions), lens [B] int64 (any order; values are clamped to [0,T]; 0 gives a zero
+ *   embedding), emb [ntoken,I] fp32, w_ih[d] [4H,I], w_hh[d] [4H,H], b_ih[d] / b_hh[d] [4H] fp32 for d = 0 (forward,
+ *   rnn.*_l0) and d = 1 (rnn.*_l0_reverse), gate order i,f,g,o; the four pointer arrays are HOST arrays of two
+ *   device pointers.  sent [B,2H] fp32.  H must be 128 (RNNEncoder.load: nhidden=256 over two directions).
+ *   workspace: dfgan_text_encoder_workspace_bytes(B,T) bytes of device memory (the input-gate pre-activations).
+ * Token ids outside [0,ntoken) read as a zero embedding (torch raises / device-asserts there).  Two launches, no
+ * host synchronisation (the reference's cap_lens.tolist() is one). */
+size_t dfgan_text_encoder_workspace_bytes(int B, int T);
+int dfgan_text_encoder_fwd(const int64_t* tokens, const int64_t* lens, const float* emb, int64_t ntoken,
+                           const float* const* w_ih, const float* const* w_hh, const float* const* b_ih,
+                           const float* const* b_hh, float* sent, void* workspace, size_t ws_bytes, int B, int T,
+                           int I, int H, dfgan_stream_t st);
+
 /* Per-launch timing of the two GEMM engines with CUDA events on the launching stream (bench.py roofline leg).
  * dfgan_profile_read: out[e*4 + {0: summed ms, 1: executed FLOPs, 2: algorithmic bytes, 3: launches}], e = 0 for
  * dfgan_conv_run, 1 for dfgan_wgrad_run; synchronises the device and clears the records. */

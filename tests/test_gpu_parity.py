@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from tools import bringup_conv, bringup_nets
+from tools import bringup_conv, bringup_nets, bringup_text
 
 pytestmark = pytest.mark.gpu
 
@@ -26,6 +26,13 @@ def test_kernel(name):
 @pytest.mark.parametrize("name", list(bringup_nets.CASES))
 def test_network(name):
     assert bringup_nets.CASES[name](), name
+
+
+@pytest.mark.parametrize("name", list(bringup_text.CASES))
+def test_text_encoder(name):
+    """Frozen caption encoder vs the committed outputs of the reference's RNNEncoder, the fp64
+    oracle and the stock torch path."""
+    assert bringup_text.CASES[name](), name
 
 
 @pytest.mark.parametrize("name", ["fprop3_b", "fprop4s2", "dgrad", "epilogue", "subpixel"])
