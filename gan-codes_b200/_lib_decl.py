@@ -12,6 +12,12 @@ class LinearItem(C.Structure):
                 ("mask", P), ("k", C.c_int32), ("n_out", C.c_int32), ("o0", C.c_int32), ("relu", C.c_int32)]
 
 
+class AugItem(C.Structure):
+    """struct dfgan_aug_item of include/dfgan_b200.h."""
+    _fields_ = [("src", P), ("pitch", L)] + [(n, C.c_int32) for n in (
+        "src_w", "src_h", "x1", "y1", "cw", "ch", "rw", "rh", "top", "left", "flip", "reserved")]
+
+
 def declare(l: C.CDLL) -> None:
     l.dfgan_pack_entry_size.argtypes = []
     l.dfgan_pack_entry_size.restype = C.c_int
@@ -19,6 +25,8 @@ def declare(l: C.CDLL) -> None:
     l.dfgan_pack_entry_bs_offset.restype = C.c_int
     l.dfgan_unpack_entry_size.argtypes = []
     l.dfgan_unpack_entry_size.restype = C.c_int
+    l.dfgan_augment_workspace_bytes.argtypes = [I, I]
+    l.dfgan_augment_workspace_bytes.restype = C.c_size_t
     l.dfgan_text_encoder_workspace_bytes.argtypes = [I, I]
     l.dfgan_text_encoder_workspace_bytes.restype = C.c_size_t
     for name, argtypes in _TABLE.items():
@@ -58,10 +66,12 @@ _TABLE: dict = {
     "dfgan_conv2d_f32_fprop": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
+    "dfgan_augment_check": [P, I],
+    "dfgan_augment": [P, P, P, P, P, C.c_size_t, I, I, P],
     "dfgan_text_encoder_fwd": [P, P, P, L, P, P, P, P, P, P, C.c_size_t, I, I, I, I, P],
 }
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
            "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size", "dfgan_pack_entry_bs_offset", "dfgan_conv_uses_image",
-           "dfgan_unpack_entry_size", "dfgan_conv_splitk_bytes", "dfgan_text_encoder_workspace_bytes",
+           "dfgan_unpack_entry_size", "dfgan_conv_splitk_bytes", "dfgan_text_encoder_workspace_bytes", "dfgan_augment_workspace_bytes",
            *_TABLE.keys()]

@@ -287,6 +287,29 @@ int dfgan_text_encoder_fwd(const int64_t* tokens, const int64_t* lens, const flo
                            const float* const* b_hh, float* sent, void* workspace, size_t ws_bytes, int B, int T,
                            int I, int H, dfgan_stream_t st);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Image side of the input pipeline for a batch of decoded RGB images, fused: the bounding-box crop of
+ * DFGANDataset._get_image (objects/dataset.py:116-126), create_loader's Resize(int(imsize*76/64)) -> RandomCrop(imsize)
+ * -> RandomHorizontalFlip (utils.py:15-19; Resize = Pillow's antialiased BILINEAR ImagingResample, restated bit-exactly)
+ * and ToTensor + Normalize(0.5, 0.5) (objects/dataset.py:28-31).  The random decisions are inputs (drawn by the caller).
+ *   item.src: uint8 [src_h][pitch bytes] with 3 interleaved channels per pixel (device memory);
+ *   (x1, y1, cw, ch): the crop rectangle inside src; (rw, rh): the size Resize produces for a cw x ch image;
+ *   (top, left): RandomCrop offset inside the resized image; flip: RandomHorizontalFlip decision.
+ *   lut256: the fp32 value ToTensor + Normalize gives each uint8 level (device, 256 floats);
+ *   out: fp32 [B][3][imsize][imsize]; workspace: dfgan_augment_workspace_bytes(B, imsize) bytes (device).
+ * items_host (optional, same content as items_dev) is validated with dfgan_augment_check before anything is
+ * launched: E_ARG for rectangles outside their image, E_SHAPE for a resized image smaller than imsize (torchvision:
+ * ValueError) or a down-scaling factor above 11.5.  Two launches, no host synchronisation. */
+typedef struct dfgan_aug_item {
+  const uint8_t* src;
+  int64_t pitch;
+  int32_t src_w, src_h, x1, y1, cw, ch, rw, rh, top, left, flip, reserved;
+} dfgan_aug_item;
+size_t dfgan_augment_workspace_bytes(int B, int imsize);
+int dfgan_augment_check(const dfgan_aug_item* item, int imsize);
+int dfgan_augment(const dfgan_aug_item* items_host, const dfgan_aug_item* items_dev, const float* lut256, float* out,
+                  void* workspace, size_t ws_bytes, int B, int imsize, dfgan_stream_t st);
+
 /* Per-launch timing of the two GEMM engines with CUDA events on the launching stream (bench.py roofline leg).
  * dfgan_profile_read: out[e*4 + {0: summed ms, 1: executed FLOPs, 2: algorithmic bytes, 3: launches}], e = 0 for
  * dfgan_conv_run, 1 for dfgan_wgrad_run; synchronises the device and clears the records. */

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from tools import bringup_conv, bringup_nets, bringup_text
+from tools import bringup_augment, bringup_conv, bringup_nets, bringup_text
 
 pytestmark = pytest.mark.gpu
 
@@ -26,6 +26,13 @@ def test_kernel(name):
 @pytest.mark.parametrize("name", list(bringup_nets.CASES))
 def test_network(name):
     assert bringup_nets.CASES[name](), name
+
+
+@pytest.mark.parametrize("name", list(bringup_augment.CASES))
+def test_augment(name):
+    """Batched image transform: bit-exact vs the committed outputs of the reference's _get_image,
+    the integer-exact oracle and the stock torchvision / Pillow pipeline."""
+    assert bringup_augment.CASES[name](), name
 
 
 @pytest.mark.parametrize("name", list(bringup_text.CASES))
