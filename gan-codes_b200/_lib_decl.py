@@ -63,6 +63,7 @@ _TABLE: dict = {
     "dfgan_gblock_small_grads": [P, P, P, P, P, P, I, P],
     "dfgan_d_hinge": [P, P, P, I, P],
     "dfgan_gp_coef": [P, P, P, I, P],
+    "dfgan_txtimg_loss": [P, I, I, L, P, I, P, I, P, P],
     "dfgan_conv2d_f32_fprop": [P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_dgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],
     "dfgan_conv2d_f32_wgrad": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P],

@@ -617,6 +617,70 @@ __global__ void __launch_bounds__(256) gp_coef_kernel(const float* __restrict__ 
   block_reduce1(part, red, loss, 1.f);
 }
 
+// Text-image loss the trainer logs every iteration (damsm/loss.py:4-26 via deep_fusion_gan/model.py:87-89, 220-223;
+// it never enters a gradient): 1 - mean_b cos(pad(mean_hw(img_b)), sent_b), where pad places the C channel means in
+// the first C of the E sentence dimensions (F.linear with eye(E, C), :17-18) and cos is the product of the two
+// F.normalize'd vectors (eps 1e-12, :20-23).
+// Stage 1: partial[(plane * kTxtSplit + s)] = sum of slice s of plane (b, c) of the fp32 NCHW image.  Every partial
+// is written by exactly one block and summed in index order by stage 2, so the result is bit-reproducible.
+constexpr int kTxtSplit = 4;
+__global__ void __launch_bounds__(kPwThreads)
+    plane_sum_kernel(const float* __restrict__ x, long long plane_len, float* __restrict__ partial) {
+  __shared__ float red[kPwThreads / 32];
+  const long long slice = plane_len / kTxtSplit;          // plane_len is a multiple of 4 * kTxtSplit (host check)
+  const float* src = x + blockIdx.y * plane_len + blockIdx.x * slice;
+  float acc = 0.f;
+  for (long long i = threadIdx.x * 4ll; i < slice; i += kPwThreads * 4ll) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+    acc += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kPwThreads / 32; ++i) s += red[i];
+    partial[blockIdx.y * kTxtSplit + blockIdx.x] = s;
+  }
+}
+// Stage 2: one block; warp w owns samples w, w + 8, ...
+__global__ void __launch_bounds__(256)
+    txtimg_loss_kernel(const float* __restrict__ partial, float inv_plane_len, int C, const float* __restrict__ sent,
+                       int E, int B, float* loss) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int nc = C < E ? C : E;
+  float wsum = 0.f;
+  for (int b = w; b < B; b += 8) {
+    const float* s = sent + static_cast<long long>(b) * E;
+    float ss = 0.f;
+    for (int e = lane; e < E; e += 32) {
+      const float v = __ldg(s + e);
+      ss += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float mm = 0.f, ms = 0.f;
+    for (int c = 0; c < nc; ++c) {
+      const float* pp = partial + (static_cast<long long>(b) * C + c) * kTxtSplit;
+      float m = 0.f;
+      for (int k = 0; k < kTxtSplit; ++k) m += __ldg(pp + k);
+      m *= inv_plane_len;
+      mm += m * m;
+      ms += m * __ldg(s + c);
+    }
+    wsum += ms / (fmaxf(sqrtf(mm), 1e-12f) * fmaxf(sqrtf(ss), 1e-12f));
+  }
+  if (lane == 0) red[w] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    *loss = 1.f - t / B;
+  }
+}
+
 }  // namespace dfgan
 
 using namespace dfgan;
@@ -808,6 +872,20 @@ int dfgan_d_hinge(const float* logits, float* loss, float* g_logits, int B, dfga
 int dfgan_gp_coef(const float* sq, float* loss, float* coef, int B, dfgan_stream_t st) {
   if (!sq || !loss || !coef || B < 1) return DFGAN_E_ARG;
   gp_coef_kernel<<<1, 256, 0, STREAM(st)>>>(sq, loss, coef, B);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  return DFGAN_OK;
+}
+
+int dfgan_txtimg_loss(const float* img, int B, int C, int64_t plane_len, const float* sent, int E, float* partial,
+                      int partial_floats, float* loss, dfgan_stream_t st) {
+  if (!img || !sent || !partial || !loss || B < 1 || C < 1 || E < 1 || plane_len < 1) return DFGAN_E_ARG;
+  if (plane_len % (4 * kTxtSplit) || (reinterpret_cast<uintptr_t>(img) & 15)) return DFGAN_E_ARG;
+  if (static_cast<int64_t>(partial_floats) < static_cast<int64_t>(B) * C * kTxtSplit) return DFGAN_E_ARG;
+  plane_sum_kernel<<<dim3(kTxtSplit, B * C), kPwThreads, 0, STREAM(st)>>>(img, plane_len, partial);
+  count_launch();
+  DFGAN_CUDA_CHECK_LAUNCH();
+  txtimg_loss_kernel<<<1, 256, 0, STREAM(st)>>>(partial, 1.f / static_cast<float>(plane_len), C, sent, E, B, loss);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
   return DFGAN_OK;

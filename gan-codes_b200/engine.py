@@ -101,7 +101,7 @@ class DFGANTrainer:
 
     def __init__(self, generator: nn.Module, discriminator: nn.Module, batch: int, lr_g: float = 1e-4,
                  lr_d: float = 4e-4, betas=(0.0, 0.9), clip: float = 5.0, world: int = 1,
-                 use_graph: Optional[bool] = None):
+                 use_graph: Optional[bool] = None, text_image_loss: bool = False):
         if not next(generator.parameters()).is_cuda:
             raise RuntimeError("DFGANTrainer: modules must live on a CUDA device (no CPU path)")
         self.G, self.D = generator, discriminator
@@ -118,6 +118,10 @@ class DFGANTrainer:
         dev = self.gs.flat.device
         co._side_streams(dev)      # created here, never inside a stream capture
         self.ones = torch.ones(batch, device=dev, dtype=F32)
+        # the text-image loss the reference's trainer logs next to the generator loss (deep_fusion_gan/model.py:
+        # 220-223 -> damsm/loss.py); opt-in, `step` then also returns "txtimg_loss"
+        self.text_image_loss = text_image_loss
+        self._txt_partial = torch.empty(4 * batch * 3, device=dev, dtype=F32) if text_image_loss else None
         self.last: Dict[str, torch.Tensor] = {}
         # The iteration is ~400 kernel launches; replaying it as ONE CUDA graph removes the host launch cost
         # (the eager path is host-bound).  Inputs are staged into static buffers, two eager iterations warm up
@@ -190,6 +194,11 @@ class DFGANTrainer:
         emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, fake, tctx))
         lg = dnet.head_forward(dpk, dp, emb, sent, hctx)
         loss = -lg.mean()
+        if self.text_image_loss:
+            # on the images of this iteration's D step (pre-update generator), like the reference (:183, :222)
+            txt = torch.empty(1, device=fake.device, dtype=F32)
+            K.txtimg_loss(fake, sent, txt, self._txt_partial)
+            self._seg_out["txtimg_loss"] = txt[0]
         g_embed, _ = dnet.head_backward(dpk, dp, hctx, self.ones * (-1.0 / b), None, False)
         g_img = dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_embed), None, True)
         self.gs.zero_grad()
@@ -250,6 +259,26 @@ class DFGANTrainer:
         self._graph_out = self._seg_out
         self.gs.frozen = self.ds.frozen = True
 
+    def _modules_stale(self) -> None:
+        """The Adam kernel writes the parameters in place without touching their autograd version counters, which
+        the drop-in modules' own operand caches are keyed on (modules._PackCache): drop those caches whenever the
+        trainer has stepped, so `generator(noise, sent)` / `discriminator.build_embeds` called between iterations
+        re-pack from the current weights."""
+        for m in (self.G, self.D):
+            cache = getattr(m, "_cache", None)
+            if cache is not None:
+                cache.key = None
+                cache.packed = None
+
+    def weights_changed(self) -> None:
+        """Call after writing the parameters from outside (load_state_dict, manual edits): re-packs the
+        tensor-core operand copies and drops the retained generator graph."""
+        with torch.no_grad():
+            self.gpk.refresh(self.gs.params)
+            self.dpk.refresh(self.ds.params)
+        self.g_ctx = {}
+        self._modules_stale()
+
     @torch.no_grad()
     def step(self, images: torch.Tensor, sentence_embeds: torch.Tensor, noise: torch.Tensor) -> Dict[str, torch.Tensor]:
         """One training iteration.  Inputs may live on the host (pinned memory recommended) or on the device:
@@ -259,6 +288,7 @@ class DFGANTrainer:
         dev = self.gs.flat.device
         if images.shape[0] != self.batch:
             raise RuntimeError(f"DFGANTrainer was built for batch {self.batch}, got {images.shape[0]}")
+        self._modules_stale()
         if self._in is None:
             mk = lambda t: torch.empty(t.shape, device=dev, dtype=F32)  # noqa: E731
             self._in = (mk(images), mk(sentence_embeds), mk(noise))
@@ -310,6 +340,7 @@ class DFGANTrainer:
     def gp_step(self, images: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
         """MA-GP discriminator update only (BASELINE config 4)."""
         dev = self.gs.flat.device
+        self._modules_stale()
         loss = self._gp_step(images.to(dev, F32).contiguous(), sentence_embeds.to(dev, F32).contiguous())
         self.ds.reduce(self.world)
         self._d_update()
@@ -352,8 +383,5 @@ class DFGANTrainer:
         self.D.load_state_dict(ck["discriminator"])
         self.gs.load_state_dict(ck["g_optimizer"])
         self.ds.load_state_dict(ck["d_optimizer"])
-        with torch.no_grad():
-            self.gpk.refresh(self.gs.params)
-            self.dpk.refresh(self.ds.params)
-        self.g_ctx = {}
+        self.weights_changed()
         return (ck["epoch"],) + ckpt.histories_of(ck)

@@ -344,6 +344,18 @@ def gp_coef(sq, loss, coef):
     _call("dfgan_gp_coef", _p(sq), _p(loss), _p(coef), sq.numel(), _s())
 
 
+def txtimg_loss(img, sent, loss, partial=None):
+    """img fp32 NCHW [B,C,H,W], sent fp32 [B,E] -> loss (1 element, overwritten) = 1 - mean cosine(padded channel
+    means, sentence embedding): the logged text-image loss of damsm/loss.py:4-26."""
+    b, c = img.shape[0], img.shape[1]
+    assert img.dtype == F32 and img.is_contiguous() and sent.dtype == F32 and sent.is_contiguous()
+    assert sent.shape[0] == b and loss.dtype == F32
+    if partial is None:
+        partial = torch.empty(4 * b * c, device=img.device, dtype=F32)
+    _call("dfgan_txtimg_loss", _p(img), b, c, img[0, 0].numel(), _p(sent), sent.shape[1], _p(partial),
+          partial.numel(), _p(loss), _s())
+
+
 def sqnorm_det(g, out, scratch):
     """out += sum(g^2) with a scheduling-independent (bit-reproducible) result; scratch: zero-initialised fp32 buffer
     of at least 4 * #SMs + 1 elements owned by the caller."""

@@ -246,11 +246,19 @@ int dfgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, con
  * dfgan_d_hinge: logits = [real (B) ; mismatched (B-1) ; fake (B)] -> hinge loss and d loss / d logits
  *   (deep_fusion_gan/model.py:175-189).
  * dfgan_gp_coef: sq[b] = |d logit / d (image, sentence)|^2 -> MA-GP loss 2 mean(clamp(sqrt(sq + 1e-8), 0, 10)^6) and
- *   coef[b] = (12 / B) n_b^4 [n_b <= 10]  (deep_fusion_gan/model.py:82-85, 203). */
+ *   coef[b] = (12 / B) n_b^4 [n_b <= 10]  (deep_fusion_gan/model.py:82-85, 203).
+ * dfgan_txtimg_loss: the text-image loss the reference's trainer logs every iteration without ever differentiating
+ *   it (damsm/loss.py:4-26, called at deep_fusion_gan/model.py:87-89, 220-223): img fp32 [B,C,plane_len] (NCHW
+ *   planes, 16-byte aligned, plane_len a multiple of 16), sent fp32 [B,E] (the sentence embeddings the iteration
+ *   already holds -- the reference re-runs the frozen text encoder for them, damsm/loss.py:14) ->
+ *   loss = 1 - mean_b <normalize(pad_E(mean over the plane of img_b)), normalize(sent_b)>.  Two launches, partial
+ *   sums in `partial` (>= 4*B*C floats, caller-owned), bit-reproducible (no atomics). */
 int dfgan_gblock_small_grads(const float* cs, const float* gamma, const float* bias2, float* g_bias2, float* g_gamma,
                              float* g_sbias, int C, dfgan_stream_t st);
 int dfgan_d_hinge(const float* logits, float* loss, float* g_logits, int B, dfgan_stream_t st);
 int dfgan_gp_coef(const float* sq, float* loss, float* coef, int B, dfgan_stream_t st);
+int dfgan_txtimg_loss(const float* img, int B, int C, int64_t plane_len, const float* sent, int E, float* partial,
+                      int partial_floats, float* loss, dfgan_stream_t st);
 
 /* ---------------------------------------------------------------------------------------------------------
  * fp32 precision tier (north_star: "1e-4 for fp32 / tf32-off"): plain CUDA-core convolution on the reference's own

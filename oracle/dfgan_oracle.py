@@ -258,6 +258,24 @@ def g_hinge_loss(d_sd: State, fake_images, sent):
     return -discriminator_logits(d_sd, discriminator_embeds(d_sd, fake_images), sent).mean()
 
 
+def text_image_loss(fake_images, sent):
+    """damsm/loss.py:4-26 with the sentence embeddings given (the reference re-runs its frozen, deterministic text
+    encoder on the same captions at :14, which returns the embeddings the iteration already holds): global average
+    pool of the image (:12), zero-padding of the 3 channel means to the embedding width (F.linear with eye, :16-18),
+    F.normalize of both (:20-21), loss = 1 - mean cosine (:23-25).  Logged by the trainer, never differentiated
+    (deep_fusion_gan/model.py:220-223, 231).  Pinned by tests/golden/txtimg_loss.json (oracle/make_shell_golden.py)."""
+    feat = fake_images.mean(dim=(2, 3))
+    e = sent.shape[1]
+    if feat.shape[1] != e:
+        pad = torch.zeros(feat.shape[0], e, dtype=feat.dtype, device=feat.device)
+        n = min(e, feat.shape[1])
+        pad[:, :n] = feat[:, :n]
+        feat = pad
+    feat = feat / feat.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    s = sent / sent.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    return 1 - (feat * s).sum(dim=1).mean()
+
+
 def clip_coef(grads: List[torch.Tensor], max_norm: float = 5.0):
     """torch.nn.utils.clip_grad_norm_ as used at deep_fusion_gan/model.py:196,209,227 (L2, all tensors)."""
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).to(grads[0].dtype)

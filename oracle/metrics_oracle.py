@@ -34,8 +34,12 @@ class StandInInception(nn.Module):
 
     def __init__(self, weights: Dict[str, np.ndarray]):
         super().__init__()
-        self.conv = nn.Conv2d(3, N_FEAT, 7, stride=4)
-        self.fc = nn.Linear(N_FEAT, N_CLASS)
+        # layer constructors draw their default init from the global generator; keep the stand-in RNG-neutral so
+        # that building it (the reference does so twice per epoch, evaluation/metrics.py:12, 67) does not shift the
+        # noise stream of the training loop around it
+        with torch.random.fork_rng(devices=[]):
+            self.conv = nn.Conv2d(3, N_FEAT, 7, stride=4)
+            self.fc = nn.Linear(N_FEAT, N_CLASS)
         self.aux_logits = True
         with torch.no_grad():
             self.conv.weight.copy_(torch.from_numpy(weights["conv_w"]))

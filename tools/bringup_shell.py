@@ -1,0 +1,188 @@
+"""GPU bring-up of the trainer shell: bodies of tests/test_zz_trainer_shell_gpu.py.
+
+    python tools/bringup_shell.py [case ...]
+
+    txtimg_kernel   dfgan_txtimg_loss (2 launches) against oracle.dfgan_oracle.text_image_loss, three shapes
+    shell_fit       the product DeepFusionGAN.fit (fused iteration as CUDA-graph replays, text-encoder kernels,
+                    resident IS/FID on the device) against the SAME class driven by the CPU oracle
+                    (tests/test_trainer_shell_cpu.py:ShellOnOracle), same loader, same seed: epoch losses, noise
+                    stream, files, checkpoint round trip through load_from_checkpoint, module path after training
+    metrics_device  evaluation.compute_is_fid on the device against the reference's committed results
+                    (tests/golden/metrics_golden.npz)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import warnings
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {}
+NTOKEN, BATCH = 50, 4
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _report(name, err, tol):
+    bad = not (err < tol)
+    print(f"  {name:55s} {err:.3e} (tol {tol:.0e}){'   <-- FAIL' if bad else ''}")
+    return not bad
+
+
+@case
+def txtimg_kernel():
+    import torch
+    from gan_codes_b200 import kernels as K
+    from oracle import dfgan_oracle as O
+    ok = True
+    g = torch.Generator().manual_seed(5)
+    for b, c, h, e in ((5, 3, 64, 256), (32, 3, 256, 256), (2, 3, 16, 8)):
+        img = torch.tanh(torch.randn(b, c, h, h, generator=g) + torch.randn(b, c, 1, 1, generator=g))
+        sent = torch.randn(b, e, generator=g) * 0.3
+        ref = float(O.text_image_loss(img.double(), sent.double()))
+        loss = torch.full((1,), -7.0, device="cuda")
+        K.txtimg_loss(img.cuda(), sent.cuda(), loss)
+        a = float(loss.item())
+        K.txtimg_loss(img.cuda(), sent.cuda(), loss)          # bit-reproducible: no atomics
+        ok &= _report(f"txtimg_loss B{b} {h}x{h} E{e} vs fp64 oracle", abs(a - ref), 2e-6)
+        ok &= _report("  second launch identical", abs(float(loss.item()) - a), 1e-30)
+    return ok
+
+
+def _loader(O, T, torch, n_batches):
+    out = []
+    for k in range(n_batches):
+        images, _, _ = O.synthetic_batch(BATCH, 256, seed=700 + k)
+        caps, lens = T.synthetic_captions(BATCH, NTOKEN, seed=30 + k)
+        perm = torch.arange(BATCH - 1, -1, -1)
+        out.append((images, caps[perm].unsqueeze(-1), lens[perm], tuple(f"img_{k}_{i}" for i in range(BATCH))))
+    return out
+
+
+@case
+def shell_fit():
+    import torch
+    warnings.filterwarnings("ignore", message="dropout option adds dropout")
+    from gan_codes_b200 import _lib
+    from gan_codes_b200 import evaluation as E
+    from gan_codes_b200.deep_fusion_gan import DeepFusionGAN
+    from oracle import dfgan_oracle as O
+    from oracle import metrics_oracle as M
+    from oracle import text_encoder_oracle as T
+    from tests.test_trainer_shell_cpu import ShellOnOracle
+    g_sd = O.init_generator_state(32, 100, gamma_range=(0.2, 1.0))
+    d_sd = O.init_discriminator_state(32, gamma_range=(0.2, 1.0), weight_scale=1.0)
+    t_sd = T.init_state(NTOKEN)
+    loader = _loader(O, T, torch, 2)
+    E.set_inception_factory(lambda: M.StandInInception(M.stand_in_weights()))
+    ok = True
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            enc = os.path.join(tmp, "text_encoder.pth")
+            torch.save(t_sd, enc)
+            runs = {}
+            for tag, cls in (("oracle", ShellOnOracle), ("product", DeepFusionGAN)):
+                d_img, d_gen = os.path.join(tmp, tag, "img"), os.path.join(tmp, tag, "gen")
+                os.makedirs(d_img), os.makedirs(d_gen)
+                m = cls(NTOKEN, enc, d_img, d_gen)
+                m.generator.load_state_dict(g_sd, strict=True)
+                m.discriminator.load_state_dict(d_sd, strict=True)
+                torch.manual_seed(99)
+                l0 = _lib.launch_count()
+                hist = m.fit(loader, num_epochs=1, auto_resume=False)
+                after = torch.randn(3)                       # position of the global host generator after fit
+                runs[tag] = (m, hist, after, sorted(os.listdir(d_gen)) + sorted(os.listdir(d_img)),
+                             _lib.launch_count() - l0)
+            (mo, ho, ao, fo, _), (mp, hp, ap, fp, launches) = runs["oracle"], runs["product"]
+            assert mp.device.type == "cuda" and mp.trainer is not None and type(mp.trainer).__name__ == "DFGANTrainer"
+            print(f"  product run: {launches} kernel launches of this library")
+            ok &= launches > 500
+            # bf16 free-running tolerances of tools/bringup_nets.py:_loss_rows for iterations after the first
+            g, d, gp, is_, fid, txt = ([h[0] for h in hh] for hh in zip(ho, hp))
+            ok &= _report("epoch d_loss (rel)", abs(d[1] - d[0]) / abs(d[0]), 3e-2)
+            ok &= _report("epoch gp_loss (rel)", abs(gp[1] - gp[0]) / abs(gp[0]), 3e-1)
+            ok &= _report("epoch g_loss (abs)", abs(g[1] - g[0]), 3e-1)
+            ok &= _report("epoch text-image loss (abs)", abs(txt[1] - txt[0]), 5e-3)
+            ok &= _report("IS on the stand-in network (rel)", abs(is_[1] - is_[0]) / is_[0], 2e-2)
+            print(f"  FID oracle-shell {fid[0]:.5f}  product {fid[1]:.5f} (8 images, rank-deficient: informational)")
+            ok &= fid[1] == fid[1] and abs(fid[1]) != float("inf")
+            ok &= _report("same position of the host generator after fit", float((ao - ap).abs().max()), 1e-30)
+            print("  files:", fp)
+            ok &= fo == fp == ["checkpoint.pt", "gen_0.pth", "fake_sample_epoch_0.png"]
+            # checkpoint round trip: a second product object restores weights and moments bit for bit
+            m2 = DeepFusionGAN(NTOKEN, enc, runs["product"][0].image_save_path, runs["product"][0].gen_path_save)
+            ret = m2.load_from_checkpoint(os.path.join(mp.gen_path_save, "checkpoint.pt"))
+            ok &= ret[0] == 0 and [len(x) for x in ret[1:]] == [1] * 6
+            same = all(torch.equal(v, m2.generator.state_dict()[k]) for k, v in mp.generator.state_dict().items())
+            same &= all(torch.equal(v, m2.discriminator.state_dict()[k]) for k, v in mp.discriminator.state_dict().items())
+            m2._ensure_trainer(BATCH)
+            same &= torch.equal(m2.trainer.ds.m, mp.trainer.ds.m) and torch.equal(m2.trainer.gs.v, mp.trainer.gs.v)
+            same &= int(m2.trainer.ds.step_count.item()) == 4 and int(m2.trainer.gs.step_count.item()) == 2
+            print("  checkpoint round trip identical:", bool(same))
+            ok &= bool(same)
+            # the drop-in module path after training sees the trained weights (operand caches are dropped)
+            noise, sent = torch.randn(BATCH, 100).cuda(), (torch.randn(BATCH, 256) * 0.3).cuda()
+            with torch.no_grad():
+                a = mp.generator(noise, sent)
+                b = mp.trainer.sample(noise, sent)
+            ok &= _report("module forward == trainer.sample after training", float((a - b).abs().max()), 1e-6)
+            # public text-image loss on arbitrary inputs
+            caps, lens = T.synthetic_captions(BATCH, NTOKEN, seed=3)
+            v = float(mp.compute_text_image_loss(a, caps.cuda(), lens.cuda()))
+            ref = float(O.text_image_loss(a.cpu().double(), T.sentence_embeds({k: x.double() for k, x in t_sd.items()},
+                                                                               caps, lens)))
+            ok &= _report("compute_text_image_loss vs oracle", abs(v - ref), 1e-5)
+            # two more epochs: the third iteration of a trainer captures the CUDA graph, the rest replay it
+            h2 = mp.fit(loader, num_epochs=3, start_epoch=1, auto_resume=False)
+            flat = [x for h in h2 for x in h]
+            print("  epochs 2-3 (graph replays): g", h2[0], "d", h2[1], "gp", h2[2], "txt", h2[5])
+            ok &= mp.trainer._graph is not None and [len(h) for h in h2] == [2] * 6
+            ok &= all(x == x and abs(x) != float("inf") for x in flat)
+            ok &= int(mp.trainer.ds.step_count.item()) == 12 and int(mp.trainer.gs.step_count.item()) == 6
+            ok &= os.path.exists(os.path.join(mp.gen_path_save, "gen_2.pth"))
+    finally:
+        E.set_inception_factory(None)
+    return ok
+
+
+@case
+def metrics_device():
+    import numpy as np
+    import torch
+    from gan_codes_b200 import evaluation as E
+    from oracle import metrics_oracle as M
+    z = np.load(os.path.join(ROOT, "tests", "golden", "metrics_golden.npz"))
+    w = {k: z[k] for k in ("conv_w", "conv_b", "fc_w", "fc_b")}
+    E.set_inception_factory(lambda: M.StandInInception(w))
+    try:
+        real, fake = M.to_images(z["real"]).cuda(), M.to_images(z["fake"]).cuda()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        i, f = E.compute_is_fid(fake, real, cuda=True, batch_size=32)
+        ok = _report("IS on cuda vs reference (rel)", abs(i - float(z["is_fake_1"])) / float(z["is_fake_1"]), 1e-4)
+        ok &= _report("FID on cuda vs reference (rel)", abs(f - float(z["fid_real_fake"])) / float(z["fid_real_fake"]), 1e-3)
+        ok &= E.inception(torch.device("cuda", torch.cuda.current_device())).net.fc.weight.is_cuda
+    finally:
+        E.set_inception_factory(None)
+    return ok
+
+
+def main(argv):
+    names = argv or list(CASES)
+    bad = []
+    for n in names:
+        print(f"[{n}]")
+        if not CASES[n]():
+            bad.append(n)
+    print("FAILED: " + ", ".join(bad) if bad else "all shell cases passed")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))
