@@ -1,0 +1,147 @@
+"""Drop-in `DFGANDataset` / `create_loader` (objects/dataset.py:15-141, utils.py:13-24) feeding the
+batched GPU image transform.
+
+The reference prepares every image inside `__getitem__` on the loader's single Python thread: PIL decode, bounding-box
+crop, antialiased resize, random crop, flip, ToTensor, Normalize (objects/dataset.py:112-129) -- ~2.2 ms per image,
+457 images/s, against the >2 700 images/s one B200 trains at.  Here `__getitem__` only decodes (PIL, the reference's
+decoder) and picks the caption; the loader's `collate_fn` hands the whole batch of decoded images to
+`augment.BatchImageTransform` (two CUDA launches, bit-identical pixels) and returns the reference's 4-tuple
+
+    (images [B,3,S,S] fp32 -- already on the GPU, captions [B,18,1] int64, caption lengths [B] int64, file names)
+
+which `prepare_data` / `DeepFusionGAN.fit` consume unchanged.  Same constructor arguments, attributes (`n_words`,
+`code2word`, `word2code`, `file_names`, `captions`, `bbox`, `embeddings_num`, `num_examples`, ...), file layout
+(`captions.pickle`, `{split}/filenames.pickle`, `bounding_boxes.txt`, `images.txt`, `birds/`), printed summary and random
+draws: captions come from numpy's global generator with the reference's calls (`randint(0, 10)`, `shuffle` for captions
+longer than 18 words), crop and flip from torch's global generator in sample order (augment.draw_crop_flip), and the
+DataLoader is the same class with the same arguments (`drop_last=True, shuffle=True`), so a seeded epoch yields the
+reference's batches bit for bit (tests/golden/dataset_golden.npz).
+
+`transform` is `None` (decoded samples only) or a `BatchImageTransform`; torchvision's per-image Compose is the
+reference's CPU path and is rejected -- this package has no CPU path for the pixels.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import numpy.random as random
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+N_STEPS = 18     # objects/dataset.py:100
+
+
+class DFGANDataset(Dataset):
+    def __init__(self, data_dir: str, split: str = "train", transform: Optional[Callable] = None):
+        if transform is not None and not hasattr(transform, "plan"):
+            raise TypeError("gan_codes_b200 DFGANDataset takes a BatchImageTransform (applied to whole batches on the "
+                            "GPU by `collate`), not a per-image torchvision transform: create_loader builds it")
+        self.split = split
+        self.data_dir = data_dir
+        self.split_dir = os.path.join(data_dir, split)
+        self.captions_path = os.path.join(self.data_dir, "captions.pickle")
+        self.filenames_path = os.path.join(self.split_dir, "filenames.pickle")
+        self.transform = transform
+        self.embeddings_num = 10
+        self.images_dir = os.path.join(self.data_dir, "birds")
+        self.bbox_path = self._locate("bounding_boxes.txt")
+        self.images_path = self._locate("images.txt")
+        self.bbox = self._load_bbox()
+        self.file_names, self.captions, self.code2word, self.word2code = self._load_text_data()
+        self.n_words = len(self.code2word)
+        self.num_examples = len(self.file_names)
+        self._print_info()
+
+    def _locate(self, name: str) -> str:
+        """data_dir, then ../data, then ./data (objects/dataset.py:35-47)."""
+        path = os.path.join(self.data_dir, name)
+        if not os.path.isfile(path):
+            path = os.path.join("..", "data", name)
+            if not os.path.isfile(path):
+                path = os.path.join(os.getcwd(), "data", name)
+        return path
+
+    def _print_info(self):
+        print(f"Total filenames: {len(self.bbox)}")
+        print(f"Load captions from: {self.captions_path}")
+        print(f"Load file names from: {self.filenames_path} ({self.num_examples})")
+        print(f"Dictionary size: {self.n_words}")
+        print(f"Embeddings number: {self.embeddings_num}")
+
+    @staticmethod
+    def _rows(path: str) -> List[List[str]]:
+        with open(path) as f:
+            return [line.split() for line in f if line.strip()]
+
+    def _load_bbox(self) -> Dict[str, List[int]]:
+        """{file name without '.jpg': [x, y, width, height] as ints} (:63-75; the i-th row of bounding_boxes.txt
+        belongs to the i-th row of images.txt, values truncated like DataFrame.astype(int))."""
+        boxes = [[int(float(v)) for v in row[1:5]] for row in self._rows(self.bbox_path)]
+        names = [row[1] for row in self._rows(self.images_path)]
+        return {name[:-4]: boxes[i] for i, name in enumerate(names)}
+
+    def _load_text_data(self) -> Tuple[List[str], List[List[int]], Dict[int, str], Dict[str, int]]:
+        with open(self.captions_path, "rb") as file:
+            train_captions, test_captions, code2word, word2code = pickle.load(file)
+        filenames = self._load_filenames()
+        return filenames, (train_captions if self.split == "train" else test_captions), code2word, word2code
+
+    def _load_filenames(self) -> List[str]:
+        if os.path.isfile(self.filenames_path):
+            with open(self.filenames_path, "rb") as file:
+                return pickle.load(file)
+        raise ValueError(f"File {self.filenames_path} does not exist")
+
+    def _get_caption(self, caption_idx: int) -> Tuple[np.ndarray, int]:
+        """:98-110: zero-padded [18,1] int64 column; longer captions keep 18 randomly chosen words in order."""
+        caption = np.array(self.captions[caption_idx])
+        pad_caption = np.zeros((N_STEPS, 1), dtype="int64")
+        if len(caption) <= N_STEPS:
+            pad_caption[:len(caption), 0] = caption
+            return pad_caption, len(caption)
+        indices = list(np.arange(len(caption)))
+        random.shuffle(indices)
+        pad_caption[:, 0] = caption[np.sort(indices[:N_STEPS])]
+        return pad_caption, N_STEPS
+
+    def _get_random_caption(self, idx: int) -> Tuple[np.ndarray, int]:
+        caption_shift = random.randint(0, self.embeddings_num)
+        return self._get_caption(idx * self.embeddings_num + caption_shift)
+
+    def _decode(self, image_path: str) -> torch.Tensor:
+        """Image.open(...).convert('RGB') (:113) as a uint8 [H, W, 3] tensor; everything after the decode is the
+        batched transform's."""
+        from PIL import Image
+        with Image.open(image_path) as im:
+            return torch.from_numpy(np.array(im.convert("RGB"), dtype=np.uint8))
+
+    def __getitem__(self, idx: int):
+        """(decoded uint8 [H,W,3], bounding box, caption [18,1], caption length, file name)."""
+        file_name = self.file_names[idx]
+        image = self._decode(f"{self.images_dir}/{file_name}.jpg")
+        encoded_caption, caption_len = self._get_random_caption(idx)
+        return image, self.bbox[file_name], encoded_caption, caption_len, file_name
+
+    def __len__(self) -> int:
+        return self.num_examples
+
+    def collate(self, samples):
+        """Batch of decoded samples -> the reference's (images, captions, captions_len, file_names) with the image
+        transform applied to the whole batch on the GPU."""
+        if self.transform is None:
+            raise RuntimeError("DFGANDataset.collate needs the BatchImageTransform (create_loader sets it)")
+        images, boxes, captions, lens, names = zip(*samples)
+        batch = self.transform(list(images), list(boxes))
+        return (batch, torch.from_numpy(np.stack(captions)), torch.tensor([int(n) for n in lens], dtype=torch.int64),
+                list(names))
+
+
+def create_loader(imsize: int, batch_size: int, data_dir: str, split: str) -> DataLoader:
+    """utils.py:13-24."""
+    assert split in ["train", "test"], "Wrong split type, expected train or test"
+    from .augment import BatchImageTransform
+    dataset = DFGANDataset(data_dir, split, BatchImageTransform(imsize))
+    return DataLoader(dataset, batch_size=batch_size, drop_last=True, shuffle=True, collate_fn=dataset.collate)

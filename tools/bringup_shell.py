@@ -9,6 +9,8 @@
                     stream, files, checkpoint round trip through load_from_checkpoint, module path after training
     metrics_device  evaluation.compute_is_fid on the device against the reference's committed results
                     (tests/golden/metrics_golden.npz)
+    loader          dataset.create_loader (decode on the host, batched GPU transform in the collate) against the
+                    reference's DataLoader batches on tests/golden/mini_cub, bit for bit
 """
 from __future__ import annotations
 
@@ -171,6 +173,35 @@ def metrics_device():
     finally:
         E.set_inception_factory(None)
     return ok
+
+
+@case
+def loader():
+    """gan_codes_b200.dataset.create_loader on tests/golden/mini_cub: two seeded epochs of the train loader and one of
+    the test loader reproduce the reference's batches (tests/golden/dataset_golden.npz) bit for bit, images on the GPU."""
+    import numpy as np
+    import torch
+    from gan_codes_b200.dataset import create_loader
+    mini = os.path.join(ROOT, "tests", "golden", "mini_cub")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "dataset_golden.npz"))
+    ok = True
+    for split, epochs in (("train", 2), ("test", 1)):
+        ld = create_loader(64, 2, mini, split)
+        torch.manual_seed(2024)
+        np.random.seed(2024)
+        k, bad = 0, 0
+        for _ in range(epochs):
+            for images, captions, lens, names in ld:
+                ok &= images.is_cuda and images.dtype == torch.float32
+                ref = torch.from_numpy(gold[f"{split}_{k}_images"]).float().div(255).sub(0.5).div(0.5)
+                bad += int((images.cpu() != ref).sum())
+                ok &= list(names) == gold[f"{split}_{k}_names"].tolist()
+                ok &= np.array_equal(captions.numpy(), gold[f"{split}_{k}_captions"])
+                ok &= np.array_equal(lens.numpy(), gold[f"{split}_{k}_lens"])
+                k += 1
+        ok &= k == int(gold[f"{split}_batches"])
+        ok &= _report(f"{split}: {k} batches, pixels differing from the reference's", float(bad), 0.5)
+    return bool(ok)
 
 
 def main(argv):
