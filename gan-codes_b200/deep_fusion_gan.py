@@ -29,8 +29,12 @@ What differs from the reference's loop, and why (each one is invisible in the re
   * batches must have the constant size of the first one (the reference's loaders are built with `drop_last=True`,
     utils.py:24); a different size raises.
 
-Data parallel: `DeepFusionGAN(..., world=N)` inside a torch.distributed process group shards nothing by itself --
-every rank feeds its own loader shard; the three gradient all-reduces happen inside DFGANTrainer.
+Data parallel (the reference has none): `DeepFusionGAN(..., world=N)` inside an initialised
+torch.distributed process group.  Every rank feeds its own shard of the data (e.g. a DistributedSampler in its loader;
+all ranks must see the same number of batches); the three gradient all-reduces per iteration happen inside
+DFGANTrainer; the epoch loss sums are averaged over the ranks with one more tiny all-reduce, so every rank holds the
+same histories and a non-finite loss stops all ranks together; IS/FID are computed by every rank on its own evaluation
+shard and rank 0's values are the ones saved; only rank 0 prints and writes files.
 """
 from __future__ import annotations
 
@@ -116,6 +120,7 @@ class DeepFusionGAN:
         self.grad_clip_g = 5.0
         self.grad_clip_d = 5.0
         self.world = world
+        self.rank = torch.distributed.get_rank() if world > 1 else 0
         self.trainer = None
         self._pin = {}
 
@@ -256,7 +261,8 @@ class DeepFusionGAN:
             txtimg_losses_epoch = checkpoint["txtimg_losses"]
             print(f"Resuming from epoch {start_epoch}")
 
-        for epoch in trange(start_epoch, num_epochs, desc="Train Deep Fusion GAN"):
+        say = print if self.rank == 0 else (lambda *a, **k: None)
+        for epoch in trange(start_epoch, num_epochs, desc="Train Deep Fusion GAN", disable=self.rank != 0):
             sums, n_iter = None, 0
             for batch in train_loader:
                 images, captions, captions_len, _ = self._prepare(batch)
@@ -270,6 +276,9 @@ class DeepFusionGAN:
                 n_iter += 1
             if n_iter == 0:
                 raise RuntimeError("train_loader produced no batches")
+            if self.world > 1:
+                torch.distributed.all_reduce(sums)
+                sums = sums / self.world
             means = (sums / n_iter).tolist()                     # the ONE device->host read of the epoch
             for name, v in zip(("generator loss", "discriminator loss", "gradient penalty loss", "text-image loss"),
                                means):
@@ -283,7 +292,7 @@ class DeepFusionGAN:
 
             with torch.no_grad():                                                               # :237-274
                 eval_loader = test_loader if test_loader is not None else train_loader
-                print(f"Computing metrics on {'test' if test_loader is not None else 'training'} set")
+                say(f"Computing metrics on {'test' if test_loader is not None else 'training'} set")
                 real_imgs_metric, fake_imgs_metric = [], []
                 for i, batch in enumerate(eval_loader):
                     if i >= 32:
@@ -300,16 +309,17 @@ class DeepFusionGAN:
                 if hasattr(self, "compute_is_fid"):
                     try:
                         is_score, fid_score = self.compute_is_fid(fake_imgs_metric, real_imgs_metric)
-                        print(f"Computed IS: {is_score:.4f}, FID: {fid_score:.4f}")
+                        say(f"Computed IS: {is_score:.4f}, FID: {fid_score:.4f}")
                     except Exception as e:
-                        print(f"Error computing metrics: {e}")
+                        say(f"Error computing metrics: {e}")
                 is_scores_epoch.append(is_score)
                 fid_scores_epoch.append(fid_score)
 
-            self._save_fake_image_with_prompt(fake_images, captions, captions_len, epoch)
-            self._save_checkpoint(epoch, g_losses_epoch, d_losses_epoch, d_gp_losses_epoch,
-                                  is_scores_epoch, fid_scores_epoch, txtimg_losses_epoch)
-            print(f"Epoch {epoch+1}: "
+            if self.rank == 0:
+                self._save_fake_image_with_prompt(fake_images, captions, captions_len, epoch)
+                self._save_checkpoint(epoch, g_losses_epoch, d_losses_epoch, d_gp_losses_epoch,
+                                      is_scores_epoch, fid_scores_epoch, txtimg_losses_epoch)
+            say(f"Epoch {epoch+1}: "
                   f"G Loss: {g_losses_epoch[-1]:.4f}, "
                   f"D Loss: {d_losses_epoch[-1]:.4f}, "
                   f"D GP Loss: {d_gp_losses_epoch[-1]:.4f}, "
