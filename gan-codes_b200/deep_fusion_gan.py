@@ -200,11 +200,8 @@ class DeepFusionGAN:
     def compute_text_image_loss(self, fake_images, captions, cap_lens):
         """:87-89 -> damsm/loss.py:4-26 for arbitrary images / captions (one encoder pass + one fused kernel).
         Inside `fit` the same quantity comes out of the iteration itself."""
-        from . import kernels as K
-        sent = self.text_encoder(captions, cap_lens)
-        loss = torch.empty(1, device=sent.device, dtype=torch.float32)
-        K.txtimg_loss(fake_images.detach().to(sent.device, torch.float32).contiguous(), sent.contiguous(), loss)
-        return loss[0]
+        from .damsm import damsm_loss
+        return damsm_loss(fake_images, captions, cap_lens, self.text_encoder)
 
     def compute_is_fid(self, fake_imgs, real_imgs):
         """:91-97, both metrics from the resident Inception network (evaluation.compute_is_fid)."""

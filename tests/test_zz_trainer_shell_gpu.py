@@ -7,6 +7,6 @@ from tools import bringup_shell
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", list(bringup_shell.CASES))
+@pytest.mark.parametrize("name", [n for n in bringup_shell.CASES if n not in bringup_shell.UNVERIFIED])
 def test_shell(name):
     assert bringup_shell.CASES[name](), f"{name} failed"

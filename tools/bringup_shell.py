@@ -204,6 +204,39 @@ def loader():
     return bool(ok)
 
 
+@case
+def train_script():
+    """gan_codes_b200.train.train on tests/golden/mini_cub with the product classes: loader -> GPU transform -> text
+    encoder -> fused iteration -> evaluation -> files, one epoch at batch 2, then a restart that finds nothing to do.
+    NOT YET RUN ON A B200 (written after the round's GPU budget was spent): tests/test_zz_trainer_shell_gpu.py skips it
+    until it has (UNVERIFIED below)."""
+    import torch
+    warnings.filterwarnings("ignore", message="dropout option adds dropout")
+    from gan_codes_b200 import evaluation as E
+    from gan_codes_b200 import train as T
+    from oracle import metrics_oracle as M
+    from oracle import text_encoder_oracle as TE
+    mini = os.path.join(ROOT, "tests", "golden", "mini_cub")
+    E.set_inception_factory(lambda: M.StandInInception(M.stand_in_weights()))
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            enc = os.path.join(tmp, "text_encoder.pth")
+            torch.save(TE.init_state(40), enc)
+            img_dir, gen_dir = os.path.join(tmp, "img"), os.path.join(tmp, "gen")
+            out = T.train(mini, enc, img_dir, gen_dir, num_epochs=1, batch_size=2)
+            ok = [len(h) for h in out] == [1] * 6 and all(x == x and abs(x) != float("inf") for h in out for x in h)
+            ok &= sorted(os.listdir(gen_dir)) == ["checkpoint.pt", "gen_0.pth"]
+            ok &= sorted(os.listdir(img_dir)) == ["fake_sample_epoch_0.png"]
+            out2 = T.train(mini, enc, img_dir, gen_dir, num_epochs=1, batch_size=2)
+            ok &= [list(h) for h in out2] == [list(h) for h in out]
+    finally:
+        E.set_inception_factory(None)
+    return bool(ok)
+
+
+UNVERIFIED = {"train_script"}
+
+
 def main(argv):
     names = argv or list(CASES)
     bad = []
