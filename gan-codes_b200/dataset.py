@@ -65,11 +65,10 @@ class DFGANDataset(Dataset):
         return path
 
     def _print_info(self):
-        print(f"Total filenames: {len(self.bbox)}")
-        print(f"Load captions from: {self.captions_path}")
-        print(f"Load file names from: {self.filenames_path} ({self.num_examples})")
-        print(f"Dictionary size: {self.n_words}")
-        print(f"Embeddings number: {self.embeddings_num}")
+        for line in (f"Total filenames: {len(self.bbox)}", f"Load captions from: {self.captions_path}",
+                     f"Load file names from: {self.filenames_path} ({self.num_examples})",
+                     f"Dictionary size: {self.n_words}", f"Embeddings number: {self.embeddings_num}"):
+            print(line)
 
     @staticmethod
     def _rows(path: str) -> List[List[str]]:
@@ -84,28 +83,27 @@ class DFGANDataset(Dataset):
         return {name[:-4]: boxes[i] for i, name in enumerate(names)}
 
     def _load_text_data(self) -> Tuple[List[str], List[List[int]], Dict[int, str], Dict[str, int]]:
-        with open(self.captions_path, "rb") as file:
-            train_captions, test_captions, code2word, word2code = pickle.load(file)
-        filenames = self._load_filenames()
-        return filenames, (train_captions if self.split == "train" else test_captions), code2word, word2code
-
-    def _load_filenames(self) -> List[str]:
-        if os.path.isfile(self.filenames_path):
-            with open(self.filenames_path, "rb") as file:
-                return pickle.load(file)
-        raise ValueError(f"File {self.filenames_path} does not exist")
+        """captions.pickle = [train captions, test captions, code2word, word2code]; `{split}/filenames.pickle` = the
+        split's file names, 10 consecutive captions each (:77-96)."""
+        if not os.path.isfile(self.filenames_path):
+            raise ValueError(f"File {self.filenames_path} does not exist")
+        with open(self.captions_path, "rb") as f:
+            by_split = pickle.load(f)
+        with open(self.filenames_path, "rb") as f:
+            names = pickle.load(f)
+        return names, by_split[0 if self.split == "train" else 1], by_split[2], by_split[3]
 
     def _get_caption(self, caption_idx: int) -> Tuple[np.ndarray, int]:
         """:98-110: zero-padded [18,1] int64 column; longer captions keep 18 randomly chosen words in order."""
-        caption = np.array(self.captions[caption_idx])
-        pad_caption = np.zeros((N_STEPS, 1), dtype="int64")
-        if len(caption) <= N_STEPS:
-            pad_caption[:len(caption), 0] = caption
-            return pad_caption, len(caption)
-        indices = list(np.arange(len(caption)))
-        random.shuffle(indices)
-        pad_caption[:, 0] = caption[np.sort(indices[:N_STEPS])]
-        return pad_caption, N_STEPS
+        words = np.asarray(self.captions[caption_idx])
+        n = len(words)
+        column = np.zeros((N_STEPS, 1), dtype="int64")
+        if n > N_STEPS:
+            order = list(np.arange(n))
+            random.shuffle(order)                          # the reference's draw: a list shuffled by numpy's generator
+            words, n = words[np.sort(order[:N_STEPS])], N_STEPS
+        column[:n, 0] = words
+        return column, n
 
     def _get_random_caption(self, idx: int) -> Tuple[np.ndarray, int]:
         caption_shift = random.randint(0, self.embeddings_num)
