@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE -- not a product path.  Only tests/ and oracle/make_metrics_golden.py import this module.
+"""TEST INFRASTRUCTURE -- not a product path.  Only tests/, tools/bringup_shell.py (the bodies of the GPU tests) and the
+golden generators oracle/make_metrics_golden.py / make_shell_golden.py import this module.
 
 CPU restatement (numpy + scipy, the libraries the reference uses) of the statistics of
 Deep_Fusion_GAN/src/evaluation/metrics.py:
