@@ -137,9 +137,54 @@ class DFGANDataset(Dataset):
                 list(names))
 
 
-def create_loader(imsize: int, batch_size: int, data_dir: str, split: str) -> DataLoader:
-    """utils.py:13-24."""
+def _as_list(samples):
+    return samples
+
+
+class _MainProcessCollate:
+    """A DataLoader whose worker processes only decode (`__getitem__` touches no CUDA state) while the batched GPU
+    transform runs in the consuming process: iterating yields `dataset.collate(samples)` for every list of decoded
+    samples the workers deliver.  Quacks like the DataLoader for what the trainer uses (`dataset`, `len`, iteration)."""
+
+    def __init__(self, loader: DataLoader, dataset: "DFGANDataset"):
+        self.loader = loader
+        self.dataset = dataset
+        self.batch_size = loader.batch_size
+
+    def __len__(self) -> int:
+        return len(self.loader)
+
+    def __iter__(self):
+        if getattr(self.loader, "_iterator", None) is not None:
+            # A DataLoader draws one number from the global generator whenever it builds an iterator (its worker base
+            # seed); with persistent workers the iterator is built once and re-armed afterwards, so later epochs would
+            # see a generator stream shifted by one draw against the single-process loader.  Spend that draw here: the
+            # shuffling order and the crops of every epoch stay those of the seeded `num_workers=0` run (checked by
+            # tests/test_dataset_cpu.py).
+            torch.empty((), dtype=torch.int64).random_()
+        for samples in self.loader:
+            yield self.dataset.collate(samples)
+
+
+def create_loader(imsize: int, batch_size: int, data_dir: str, split: str, num_workers: int = 0):
+    """utils.py:13-24.  `num_workers=0` is the reference's loader (one thread decodes; a seeded epoch reproduces the
+    reference's batches exactly).  PIL decodes ~250 CUB photographs per second per core, a tenth of what one B200
+    trains at, so production runs pass `num_workers > 0`: the JPEG decode and the caption choice move to worker
+    processes, the crop / flip draws and the GPU transform stay in this process.  Sample order, crops and flips (torch
+    generator of this process) are then still those of the seeded reference run; the caption picked for an image is
+    not (numpy's generator lives in the workers)."""
     assert split in ["train", "test"], "Wrong split type, expected train or test"
     from .augment import BatchImageTransform
     dataset = DFGANDataset(data_dir, split, BatchImageTransform(imsize))
-    return DataLoader(dataset, batch_size=batch_size, drop_last=True, shuffle=True, collate_fn=dataset.collate)
+    return make_loader(dataset, batch_size, num_workers)
+
+
+def make_loader(dataset: DFGANDataset, batch_size: int, num_workers: int = 0):
+    if num_workers <= 0:
+        return DataLoader(dataset, batch_size=batch_size, drop_last=True, shuffle=True, collate_fn=dataset.collate)
+    import copy
+    decode_only = copy.copy(dataset)        # what the workers receive: no transform, hence no CUDA object to fork / pickle
+    decode_only.transform = None
+    return _MainProcessCollate(DataLoader(decode_only, batch_size=batch_size, drop_last=True, shuffle=True,
+                                          collate_fn=_as_list, num_workers=num_workers, persistent_workers=True,
+                                          prefetch_factor=4), dataset)

@@ -13,7 +13,7 @@ import torch
 from torch.utils.data import DataLoader
 
 from gan_codes_b200 import augment as P
-from gan_codes_b200.dataset import DFGANDataset, create_loader
+from gan_codes_b200.dataset import DFGANDataset, create_loader, make_loader
 from oracle import augment_oracle as A
 
 HERE = os.path.dirname(__file__)
@@ -120,3 +120,28 @@ def test_errors():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="CUDA only"):
             create_loader(64, 2, MINI, "train")
+
+
+def test_worker_processes_decode_and_the_main_process_transforms(gold):
+    """num_workers > 0: same sample order, crops, flips and pixels as the seeded single-process run (all drawn from this
+    process's torch generator); only the caption choice moves to the workers' numpy generators."""
+    ds = DFGANDataset(MINI, "train", OracleTransform(IMSIZE))
+    ld = make_loader(ds, BATCH, num_workers=2)
+    assert len(ld) == 2 and ld.dataset is ds and ld.batch_size == BATCH
+    torch.manual_seed(SEED)
+    np.random.seed(SEED)
+    k = 0
+    for _ in range(2):
+        for images, captions, lens, names in ld:
+            assert list(names) == gold[f"train_{k}_names"].tolist()
+            assert np.array_equal(levels(images), gold[f"train_{k}_images"])
+            assert captions.shape == (BATCH, 18, 1) and captions.dtype == torch.int64 and lens.dtype == torch.int64
+            for b, name in enumerate(names):                      # one of the image's ten captions, correctly padded
+                idx = ds.file_names.index(name)
+                n = int(lens[b])
+                cands = [c for c in ds.captions[idx * 10:(idx + 1) * 10] if min(len(c), 18) == n]
+                row = captions[b, :n, 0].tolist()
+                assert any(row == list(c) if len(c) <= 18 else set(row) <= set(c) for c in cands)
+                assert (captions[b, n:, 0] == 0).all()
+            k += 1
+    assert k == 4
