@@ -4,6 +4,7 @@
 after the checkpoint's (the reference script repeats the checkpoint's epoch, see the comment in `train`).
 
     python -m gan_codes_b200.train --data /data/birds --encoder /weights/text_encoder.pth [--epochs 600] [--batch 24]
+                                   [--workers 12]
 """
 from __future__ import annotations
 
@@ -28,14 +29,15 @@ def fix_seed(seed: int = 123321):
 
 def train(data_path: str, encoder_weights_path: str, image_save_path: str = "../gen_images",
           gen_path_save: str = "../gen_weights", num_epochs: int = 600, batch_size: int = 24,
-          imsize: int = 256) -> Tuple[List[float], ...]:
+          imsize: int = 256, num_workers: int = 0) -> Tuple[List[float], ...]:
     from .dataset import create_loader
     from .deep_fusion_gan import DeepFusionGAN
     fix_seed()
     os.makedirs(image_save_path, exist_ok=True)
     os.makedirs(gen_path_save, exist_ok=True)
-    train_loader = create_loader(imsize, batch_size, data_path, "train")
-    test_loader = create_loader(imsize, batch_size, data_path, "test")
+    extra = {"num_workers": num_workers} if num_workers else {}          # 0 = the reference's single-thread loader
+    train_loader = create_loader(imsize, batch_size, data_path, "train", **extra)
+    test_loader = create_loader(imsize, batch_size, data_path, "test", **extra)
     print(f"Test set size: {len(test_loader.dataset)} images")
     model = DeepFusionGAN(n_words=train_loader.dataset.n_words, encoder_weights_path=encoder_weights_path,
                           image_save_path=image_save_path, gen_path_save=gen_path_save)
@@ -73,8 +75,9 @@ def main() -> None:
     ap.add_argument("--epochs", type=int, default=600)
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--imsize", type=int, default=256)
+    ap.add_argument("--workers", type=int, default=0, help="decode worker processes per loader (0 = reference behaviour)")
     a = ap.parse_args()
-    train(a.data, a.encoder, a.images_out, a.weights_out, a.epochs, a.batch, a.imsize)
+    train(a.data, a.encoder, a.images_out, a.weights_out, a.epochs, a.batch, a.imsize, a.workers)
 
 
 if __name__ == "__main__":
