@@ -82,6 +82,15 @@ class _PinnedStage:
         ev.record()
         return dev
 
+    def fill_only(self, fill: Callable[[Tensor], None]):
+        """(pinned buffer, its event): the consumer copies from the buffer itself and records the event on the stream
+        it copied on (DFGAN_STAGE_MIXED: DFGANTrainer.step stages host tensors on its own copy stream)."""
+        buf, ev = self.slots[self.i]
+        self.i ^= 1
+        ev.synchronize()
+        fill(buf)
+        return buf, ev
+
 
 class _PendingAdam:
     """`g_optim` / `d_optim` before the first batch fixes the batch size (the flat optimiser lives in
@@ -123,6 +132,10 @@ class DeepFusionGAN:
         self.rank = torch.distributed.get_rank() if world > 1 else 0
         self.trainer = None
         self._pin = {}
+        # opt-in, not yet measured: leave the sorted image batch in pinned host memory and let DFGANTrainer.step copy
+        # it on its side stream, overlapping the previous iteration
+        self._overlap_h2d = os.environ.get("DFGAN_STAGE_MIXED", "0") == "1"
+        self._h2d_done = None
 
     # ------------------------------------------------------------------------------------ engine plumbing
     def _make_trainer(self, batch_size: int):
@@ -163,15 +176,19 @@ class DeepFusionGAN:
             self._pin[key] = _PinnedStage(shape, dtype, self.device)
         return self._pin[key]
 
-    def _prepare(self, batch):
+    def _prepare(self, batch, overlap: bool = False):
         """prepare_data (objects/utils.py:7-20) with the image gather written straight into pinned memory and an
         asynchronous copy (25 MB per batch of 32): the host never waits for the transfer."""
         images, captions, captions_len, file_names = batch
         if self.device.type != "cuda" or images.is_cuda or images.dtype != torch.float32:
             return prepare_data(batch, self.device)
         sorted_cap_lens, sorted_cap_indices = torch.sort(captions_len, 0, True)
-        sorted_images = self._stage("images", images.shape, images.dtype).push(
-            lambda buf: torch.index_select(images, 0, sorted_cap_indices, out=buf))
+        stage = self._stage("images", images.shape, images.dtype)
+        gather = lambda buf: torch.index_select(images, 0, sorted_cap_indices, out=buf)  # noqa: E731
+        if overlap:
+            sorted_images, self._h2d_done = stage.fill_only(gather)      # stays on the host; see `_step`
+        else:
+            sorted_images = stage.push(gather)
         sorted_captions = captions[sorted_cap_indices].squeeze().to(self.device)
         sorted_file_names = [file_names[i] for i in sorted_cap_indices.numpy()]
         return sorted_images, sorted_captions, sorted_cap_lens.to(self.device), sorted_file_names
@@ -262,12 +279,12 @@ class DeepFusionGAN:
         for epoch in trange(start_epoch, num_epochs, desc="Train Deep Fusion GAN", disable=self.rank != 0):
             sums, n_iter = None, 0
             for batch in train_loader:
-                images, captions, captions_len, _ = self._prepare(batch)
+                images, captions, captions_len, _ = self._prepare(batch, overlap=self._overlap_h2d)
                 batch_size = images.shape[0]
                 trainer = self._ensure_trainer(batch_size)
                 sentence_embeds = self.text_encoder(captions, captions_len).detach()            # :171
                 noise = self._draw_noise(batch_size)                                            # :182
-                out = trainer.step(images, sentence_embeds, noise)                              # :173-228
+                out = self._step(trainer, images, sentence_embeds, noise)                       # :173-228
                 row = torch.stack([out[k] if k in out else out["g_loss"] * 0 for k in LOSS_KEYS]).double()
                 sums = row if sums is None else sums + row
                 n_iter += 1
@@ -325,6 +342,13 @@ class DeepFusionGAN:
                   f"FID: {fid_scores_epoch[-1]:.4f}")
 
         return g_losses_epoch, d_losses_epoch, d_gp_losses_epoch, is_scores_epoch, fid_scores_epoch, txtimg_losses_epoch
+
+    def _step(self, trainer, images: Tensor, sentence_embeds: Tensor, noise: Tensor):
+        out = trainer.step(images, sentence_embeds, noise)
+        if self._h2d_done is not None:          # images were handed over as a pinned host buffer (DFGAN_STAGE_MIXED)
+            self._h2d_done.record(trainer._copy_stream)
+            self._h2d_done = None
+        return out
 
     def _generate(self, noise: Tensor, sentence_embeds: Tensor) -> Tensor:
         """self.generator(noise, sentence_embeds) under no_grad (:258) on the trainer's packed weights."""

@@ -27,6 +27,7 @@ from . import dnet, gnet
 from . import kernels as K
 
 F32, BF16 = torch.float32, torch.bfloat16
+STAGE_MIXED = os.environ.get("DFGAN_STAGE_MIXED", "0") == "1"
 
 
 class FlatState:
@@ -309,6 +310,21 @@ class DFGANTrainer:
             main.wait_event(self._ev_h2d)
             for dst, src in zip(self._in, self._stage):
                 dst.copy_(src, non_blocking=True)
+            self._ev_free.record()
+        elif STAGE_MIXED and any(not t.is_cuda for t in srcs):
+            # opt-in (DFGAN_STAGE_MIXED=1, not yet measured): host tensors among device tensors take the same
+            # overlapping route as the all-host case, device tensors are copied on the main stream as below
+            host = [not t.is_cuda for t in srcs]
+            main = torch.cuda.current_stream()
+            self._copy_stream.wait_event(self._ev_free)
+            with torch.cuda.stream(self._copy_stream):
+                for dst, src, h in zip(self._stage, srcs, host):
+                    if h:
+                        dst.copy_(src, non_blocking=True)
+                self._ev_h2d.record()
+            main.wait_event(self._ev_h2d)
+            for dst, st, src, h in zip(self._in, self._stage, srcs, host):
+                dst.copy_(st if h else src, non_blocking=True)
             self._ev_free.record()
         else:
             for dst, src in zip(self._in, srcs):

@@ -28,7 +28,10 @@ def main() -> int:
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--decoded", type=int, default=1)
+    ap.add_argument("--overlap", type=int, default=0, help="1: DFGAN_STAGE_MIXED (images staged by the trainer's copy stream)")
     a = ap.parse_args()
+    if a.overlap:
+        os.environ["DFGAN_STAGE_MIXED"] = "1"
     import torch
     warnings.filterwarnings("ignore", message="dropout option adds dropout")
     from gan_codes_b200.deep_fusion_gan import DeepFusionGAN
@@ -36,7 +39,7 @@ def main() -> int:
     B, n_words = a.batch, 5450
     torch.manual_seed(123321)
     gen = torch.Generator().manual_seed(1)
-    out = {"batch": B, "iters": a.iters}
+    out = {"batch": B, "iters": a.iters, "overlap": a.overlap}
     with tempfile.TemporaryDirectory() as tmp:
         enc = os.path.join(tmp, "text_encoder.pth")
         torch.save(RNNEncoder(n_words, nhidden=256).state_dict(), enc)
@@ -53,10 +56,10 @@ def main() -> int:
             sums = None
             t0 = time.perf_counter()
             for i in range(n):
-                imgs, c, cl, _ = model._prepare(batches(i))
+                imgs, c, cl, _ = model._prepare(batches(i), overlap=model._overlap_h2d)
                 tr = model._ensure_trainer(imgs.shape[0])
                 sent = model.text_encoder(c, cl).detach()
-                o = tr.step(imgs, sent, model._draw_noise(imgs.shape[0]))
+                o = model._step(tr, imgs, sent, model._draw_noise(imgs.shape[0]))
                 row = torch.stack([o[k] for k in ("g_loss", "d_loss", "gp_loss", "txtimg_loss")]).double()
                 sums = row if sums is None else sums + row
             means = (sums / n).tolist()
