@@ -7,8 +7,9 @@ batch 64; configs[4]: generator sampling at batch 256), where the CPU oracle can
                   in a 4-image batch (the forward has no cross-sample term and no split accumulation: bit-exact), and
                   the first 4 match the fp32 oracle to the bf16 tolerance
     gp_step_b64   MA-GP at batch 64: the loss is the mean of the per-sample penalties, so it equals the mean over 16
-                  chunks of 4 of the ORACLE's loss; the flat gradient equals the mean of the 16 chunk gradients of the
-                  batch-4 program (linearity in the batch), and `gp_step` applies exactly one clipped Adam update of it
+                  chunks of 4 of the batch-4 program's loss (four of which are checked against the ORACLE); the flat
+                  gradient equals the mean of the 16 chunk gradients (linearity in the batch), and `gp_step` applies
+                  exactly one clipped Adam update of it
 
 NOT YET RUN ON A B200 (written after round 1's GPU budget was spent); tests/test_zz_trainer_shell_gpu.py does not
 include these cases until they have been (UNVERIFIED).
