@@ -882,6 +882,7 @@ int dfgan_txtimg_loss(const float* img, int B, int C, int64_t plane_len, const f
   if (!img || !sent || !partial || !loss || B < 1 || C < 1 || E < 1 || plane_len < 1) return DFGAN_E_ARG;
   if (plane_len % (4 * kTxtSplit) || (reinterpret_cast<uintptr_t>(img) & 15)) return DFGAN_E_ARG;
   if (static_cast<int64_t>(partial_floats) < static_cast<int64_t>(B) * C * kTxtSplit) return DFGAN_E_ARG;
+  if (static_cast<int64_t>(B) * C > 65535) return DFGAN_E_SHAPE;        // planes are the grid's y dimension
   plane_sum_kernel<<<dim3(kTxtSplit, B * C), kPwThreads, 0, STREAM(st)>>>(img, plane_len, partial);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();
