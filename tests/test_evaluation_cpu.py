@@ -107,3 +107,27 @@ def test_failure_values(gold, capsys):
         E.set_inception_factory(lambda: M.StandInInception(gold["w"]))
     out = capsys.readouterr().out
     assert "Error in IS calculation: no weights offline" in out and "Exception in FID calculation" in out
+
+
+def test_real_inception_architecture_pooled_features_and_logits():
+    """torchvision's Inception-v3 layer graph with random weights (the pretrained file cannot be downloaded): the
+    resident wrapper's pooled features equal what the reference's `model.fc = Identity()` network returns (:70-72),
+    and its logits equal the unmodified network's (:12, 31) -- one pass instead of two."""
+    import copy
+    from torchvision.models import inception_v3
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(0)
+        net = inception_v3(weights=None, aux_logits=True, transform_input=False, init_weights=False).eval()
+    ref_logits_net = copy.deepcopy(net)
+    ref_feat_net = copy.deepcopy(net)
+    ref_feat_net.fc = torch.nn.Identity()
+    ref_feat_net.aux_logits = False
+    E.set_inception_factory(lambda: net)
+    try:
+        x = torch.rand(3, 3, 299, 299, generator=torch.Generator().manual_seed(1))
+        logits, pooled = E.inception(torch.device("cpu"))(x)
+        with torch.no_grad():
+            assert pooled.shape == (3, 2048) and torch.equal(pooled, ref_feat_net(x))
+            assert logits.shape == (3, 1000) and torch.equal(logits, ref_logits_net(x))
+    finally:
+        E.set_inception_factory(None)
