@@ -7,9 +7,10 @@ clip+Adam updates -- deep_fusion_gan/model.py:173-228) at 256x256, n_channels 32
 N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.  `value` = whole-job images/s
 with inputs resident in HBM; `e2e` = the same through DFGANTrainer.step with pinned HOST inputs and a device->host
 read of the three losses every step.  `roofline` is measured live with CUDA events around every launch of the
-dominant kernel; `cpu_baseline` times the oracle port of the reference's step on the host cores (rank 0, N=1).
-`--impl reference` times that CPU path alone (the reference is PyTorch-eager CPU code; it cannot travel to the GPU
-box, oracle/ is its pinned restatement).
+dominant kernel; `cpu_baseline` times the UNMODIFIED reference trainer's own `fit` loop (oracle/_ref, vendored by
+oracle/vendor_ref.py; the oracle port only when that copy is absent) on the host cores (rank 0, N=1);
+`library_baseline` times the same reference on the B200 under stock PyTorch-CUDA (fp32, TF32, autocast bf16) -- the
+library bar.  `--impl reference` times the CPU path alone.
 """
 from __future__ import annotations
 
@@ -68,11 +69,19 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference_step(batch: int, size: int, steps: int, warmup: int):
-    """The reference's training iteration on the host cores (oracle port), returns (img/s, cores, seconds)."""
+    """The reference's training iteration on the host cores.  Returns (img/s, cores, seconds, best step, kind, what):
+    kind "reference" = the UNMODIFIED reference trainer's own `fit` loop from oracle/_ref (oracle/ref_runner.py);
+    kind "port" = oracle/dfgan_oracle.py train_step, only when oracle/_ref is absent or the size is not 256."""
     import torch
     from oracle import dfgan_oracle as O
+    from oracle import ref_runner
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if size == 256 and ref_runner.available():
+        r = ref_runner.run_fit("cpu", batch, steps, warmup, "fp32", threads=cores)
+        return (r["images_per_s"], cores, r["seconds"], r["best_ms"] / 1e3, "reference",
+                "unmodified reference DeepFusionGAN.fit loop (oracle/_ref: text encoder + D hinge + MA-GP + G, "
+                "clip, torch.optim.Adam, fp32, torch CPU)")
     depth = {256: 6, 128: 5, 64: 4}[size]
     g_sd = O.init_generator_state(32, 100, depth=depth)
     d_sd = O.init_discriminator_state(32, depth=depth)
@@ -87,7 +96,7 @@ def cpu_reference_step(batch: int, size: int, steps: int, warmup: int):
         dt = time.perf_counter() - t0
         total += dt
         best = dt if best is None else min(best, dt)
-    return batch * steps / total, cores, total, best
+    return batch * steps / total, cores, total, best, "port", "oracle/dfgan_oracle.py train_step (fp32, torch CPU)"
 
 
 def run_reference(args):
@@ -96,7 +105,8 @@ def run_reference(args):
         return
     b = 4
     t0 = time.perf_counter()
-    ips, cores, total, best = cpu_reference_step(b, args.size, max(1, args.steps), max(0, min(args.warmup, 1)))
+    ips, cores, total, best, kind, what = cpu_reference_step(b, args.size, max(1, args.steps),
+                                                             max(0, min(args.warmup, 1)))
     line = {
         "impl": "reference", "metric": "train images/sec (G+D step, 256x256)", "value": round(ips, 4),
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -104,9 +114,9 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"DF-GAN full training iteration {args.size}x{args.size}, n_channels 32, "
                                f"CPU sample batch {b}", "batch_per_gpu": b},
-        "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": f"{args.steps} iterations of batch {b} at {args.size}x{args.size} "
-                                   f"({total:.1f} s), oracle/dfgan_oracle.py train_step"},
+                                   f"({total:.1f} s), {what}"},
         "e2e": {"value": round(ips, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": round(time.perf_counter() - t0, 1),
     }
@@ -226,6 +236,7 @@ def run_ours(args):
         value = B * world * args.steps / (ms / 1e3)
         e2e = B * world * args.steps / (ms_e2e / 1e3)
         dom = max(("conv", "wgrad"), key=lambda k: prof[k]["ms"])
+        gflop_exec = (prof["conv"]["flops"] + prof["wgrad"]["flops"]) / args.steps / B / 1e9
         p = prof[dom]
         ach = p["flops"] / (p["ms"] / 1e3) / 1e12 if p["ms"] > 0 else 0.0
         traffic = None
@@ -243,7 +254,17 @@ def run_ours(args):
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 2 GB) far exceeds the 126 MB L2; no flush needed",
                        "pct_of_bf16_peak_algorithmic": round(100 * value / world * GFLOP_PER_IMAGE / 1e3 / tf_sust, 2),
-                       "gflop_per_image_algorithmic": GFLOP_PER_IMAGE, "losses": losses,
+                       "gflop_per_image_algorithmic": GFLOP_PER_IMAGE,
+                       # executed = what the two GEMM engines actually multiplied (sub-pixel folding and the pooled
+                       # shortcut save work; never credited), counted live by the launch counters of the eager pass
+                       "gflop_per_image_executed": round(gflop_exec, 2),
+                       "pct_of_bf16_peak": {
+                           "executed_flops_vs_sustained": round(100 * value / world * gflop_exec / 1e3 / tf_sust, 2),
+                           "executed_flops_vs_burst": round(100 * value / world * gflop_exec / 1e3 / tf_burst, 2),
+                           "algorithmic_flops_vs_sustained": round(100 * value / world * GFLOP_PER_IMAGE / 1e3 / tf_sust, 2),
+                           "algorithmic_flops_vs_burst": round(100 * value / world * GFLOP_PER_IMAGE / 1e3 / tf_burst, 2),
+                           "peaks_tflops": {"sustained": tf_sust, "burst": tf_burst, "source": how}},
+                       "losses": losses,
                        "cuda_graph": bool(trainer._graph is not None)},
             "e2e": {"value": round(e2e, 2), "unit": "images/s",
                     "h2d_bytes_per_step": int(images_h.numel() * 4 + sent_h.numel() * 4 + noise_h.numel() * 4),
@@ -267,13 +288,79 @@ def run_ours(args):
                          "other_engine": {k: round(v, 3) for k, v in prof["wgrad" if dom == "conv" else "conv"].items()}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            ips, cores, total, best = cpu_reference_step(4, S, 3, 1)
-            line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": f"3 iterations of batch 4 at {S}x{S} ({total:.1f} s) of "
-                                              "oracle/dfgan_oracle.py train_step (fp32, torch CPU)"}
+            ips, cores, total, best, kind, what = cpu_reference_step(4, S, 3, 1)
+            line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": kind,
+                                    "sample": f"3 iterations of batch 4 at {S}x{S} ({total:.1f} s) of {what}"}
+        if world == 1 and not args.no_library_baseline:
+            del trainer
+            torch.cuda.empty_cache()
+            line["library_baseline"] = library_baseline(B, S)
+            best = line["library_baseline"].get("value")
+            if best:
+                line["vs_library"] = {"value_ratio": round(value / best, 2), "e2e_ratio": round(e2e / best, 2),
+                                      "note": "this repo's images/s over the best stock PyTorch-CUDA mode of the "
+                                              "unmodified reference on the same B200, same batch"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def library_baseline(batch: int, size: int, steps: int = 5, warmup: int = 3) -> dict:
+    """SURVEY 2c / 8(d), BASELINE.md 5.2: the reference as it is, on this B200, under stock PyTorch-CUDA (cuDNN /
+    cuBLAS) -- fp32 with TF32 off, TF32 on, and autocast(bf16) + channels_last.  The best of the three is the bar the
+    hand-written sm_100a kernels have to beat.  oracle/_ref (the vendored unmodified reference) when present, else
+    the oracle port's train_step on the device."""
+    import torch
+    from oracle import ref_runner
+    modes, out = {}, {"unit": "images/s", "batch": batch, "steps": steps, "warmup": warmup}
+    if size == 256 and ref_runner.available():
+        out["kind"] = "reference"
+        out["what"] = "unmodified reference DeepFusionGAN.fit loop (oracle/_ref) on cuda:0, stock PyTorch kernels"
+        for mode in ref_runner.MODES:
+            try:
+                r = ref_runner.run_fit("cuda", batch, steps, warmup, mode)
+                modes[mode] = {"images_per_s": round(r["images_per_s"], 1), "ms_per_step": round(r["ms_per_step"], 2)}
+            except Exception as e:   # a mode stock PyTorch cannot run is reported, not hidden
+                modes[mode] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+            torch.cuda.empty_cache()
+    else:
+        from oracle import dfgan_oracle as O
+        out["kind"] = "port"
+        out["what"] = "oracle/dfgan_oracle.py train_step on cuda:0 (torch ops -> cuDNN / cuBLAS)"
+        depth = {256: 6, 128: 5, 64: 4}[size]
+        for mode in ref_runner.MODES:
+            try:
+                tf32 = mode == "tf32"
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.benchmark = mode.endswith("cudnn_benchmark")
+                g_sd = O.to(O.init_generator_state(32, 100, depth=depth), device="cuda")
+                d_sd = O.to(O.init_discriminator_state(32, depth=depth), device="cuda")
+                images, sent, noise = (t.cuda() for t in O.synthetic_batch(batch, size))
+                go, do = O.AdamState(g_sd, 1e-4), O.AdamState(d_sd, 4e-4)
+                import contextlib
+                ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode.startswith("bf16") else contextlib.nullcontext()
+                with ctx:
+                    for _ in range(warmup):
+                        O.train_step(g_sd, d_sd, go, do, images, sent, noise)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(steps):
+                        O.train_step(g_sd, d_sd, go, do, images, sent, noise)
+                    torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                modes[mode] = {"images_per_s": round(batch * steps / dt, 1), "ms_per_step": round(1e3 * dt / steps, 2)}
+            except Exception as e:
+                modes[mode] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+            finally:
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.benchmark = False
+            torch.cuda.empty_cache()
+    out["modes"] = modes
+    ok = {k: v["images_per_s"] for k, v in modes.items() if "images_per_s" in v}
+    if ok:
+        out["best_mode"] = max(ok, key=ok.get)
+        out["value"] = ok[out["best_mode"]]
+    return out
 
 
 def run_side_workload(args):
@@ -343,6 +430,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--workload", default="full", choices=["full", "gp", "sample"],
                     help="full = headline training iteration (BASELINE configs[1]/[2]); gp = MA-GP discriminator "
                          "update only (configs[3], default batch 64 split over the ranks); sample = no_grad generator "

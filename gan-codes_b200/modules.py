@@ -182,6 +182,12 @@ class Generator(_PrecisionMixin, nn.Module):
         _require_cuda(tensors[0], "Generator.forward")
         if self._precision == "fp32":
             return fp32.generator_forward(self, noise_vector, sentence_embed)
+        if torch.is_grad_enabled() and (noise_vector.requires_grad or sentence_embed.requires_grad):
+            # the tensor-core program produces parameter gradients only (the trainer feeds detached inputs,
+            # deep_fusion_gan/model.py:171,182); returning None here would be a silent zero gradient
+            raise RuntimeError("Generator.forward (bf16 tensor-core path): gradients with respect to noise_vector / "
+                               "sentence_embed are not produced; detach the inputs, or use "
+                               "set_precision('fp32'), whose autograd graph reaches them")
         return _GeneratorFn.apply(self, noise_vector, sentence_embed, *tensors)
 
 

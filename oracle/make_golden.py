@@ -169,6 +169,50 @@ def make(name):
     print(name, len(out), "tensors ->", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_phases(name="native_b2_fp64_phases", ws=2.0, batch=2):
+    """fp64 arbiter for the per-phase gradients at the native size: the reference's modules in float64, every phase
+    of deep_fusion_gan/model.py:173-228 evaluated FROM THE SAME WEIGHTS (no optimiser step in between), so a GPU path
+    can be held to 1e-4 on each phase without the +-lr sign chaos of Adam(beta1 = 0) on noise-level gradient
+    elements separating the two trajectories.  Same call sequence on the modules as ref_step."""
+    dt = torch.float64
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 8)
+    g_sd = O.init_generator_state(32, 100, gamma_range=(0.2, 1.0), dtype=dt)
+    d_sd = O.init_discriminator_state(32, gamma_range=(0.2, 1.0), weight_scale=ws, dtype=dt)
+    images, sent, noise = O.synthetic_batch(batch, 256, dtype=dt)
+    G, D = ref_modules(g_sd, d_sd, 6)
+    out = {"config": np.array([ws, batch], dtype=np.float64)}
+    b = batch
+    real_embeds = D.build_embeds(images)
+    d_loss_real = F.relu(1.0 - D.get_logits(real_embeds, sent)).mean()
+    d_loss_mis = F.relu(1.0 + D.get_logits(real_embeds[:b - 1], sent[1:b])).mean()
+    fake = G(noise, sent)
+    d_loss_fake = F.relu(1.0 + D.get_logits(D.build_embeds(fake.detach()), sent)).mean()
+    d_loss = d_loss_real + (d_loss_fake + d_loss_mis) / 2.0
+    D.zero_grad(); G.zero_grad()
+    d_loss.backward()
+    for k, p in D.named_parameters():
+        out[f"phase/d_grad/{k}"] = digest(p.grad)
+    out["phase/d_loss"], out["phase/fake"] = digest(d_loss), digest(fake)
+    n, grads = ref_compute_gp(D, images, sent)
+    gp = 2.0 * torch.mean(n ** 6)
+    out["phase/gp_n"], out["phase/gp_gx"], out["phase/gp_gs"] = digest(n), digest(grads[0]), digest(grads[1])
+    D.zero_grad(); G.zero_grad()
+    gp.backward()
+    for k, p in D.named_parameters():
+        out[f"phase/gp_grad/{k}"] = digest(p.grad)
+    out["phase/gp_loss"] = digest(gp)
+    g_loss = -D.get_logits(D.build_embeds(fake), sent).mean()
+    D.zero_grad(); G.zero_grad()
+    g_loss.backward()
+    for k, p in G.named_parameters():
+        out[f"phase/g_grad/{k}"] = digest(p.grad)
+    out["phase/g_loss"] = digest(g_loss)
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, len(out), "tensors ->", path, os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or CASES):
-        make(n)
+    for n in (sys.argv[1:] or list(CASES) + ["native_b2_fp64_phases"]):
+        make_phases() if n == "native_b2_fp64_phases" else make(n)

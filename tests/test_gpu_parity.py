@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from tools import bringup_augment, bringup_conv, bringup_nets, bringup_text
+from tools import bringup_augment, bringup_configs, bringup_conv, bringup_nets, bringup_parity, bringup_text
 
 pytestmark = pytest.mark.gpu
 
@@ -26,6 +26,20 @@ def test_kernel(name):
 @pytest.mark.parametrize("name", list(bringup_nets.CASES))
 def test_network(name):
     assert bringup_nets.CASES[name](), name
+
+
+@pytest.mark.parametrize("name", list(bringup_parity.CASES))
+def test_full_size_parity(name):
+    """BASELINE configs[1] / [3] / [4] at their full batch sizes against the oracle run on the same device in fp32
+    (TF32 off), the free-running bf16 gradient bound, and the committed digests of the unmodified reference's step."""
+    assert bringup_parity.CASES[name](), name
+
+
+@pytest.mark.parametrize("name", list(bringup_configs.CASES))
+def test_full_size_properties(name):
+    """Size-independent properties at batch 64 / 256 (rows of a big batch == the same rows of a small batch, mean of
+    chunk gradients, one clipped Adam update)."""
+    assert bringup_configs.CASES[name](), name
 
 
 @pytest.mark.parametrize("name", list(bringup_augment.CASES))
@@ -106,3 +120,18 @@ def test_shape_errors_match_reference_behaviour():
         D.get_logits(torch.randn(2, 512, 4, 4, device="cuda"), torch.randn(2, 128, device="cuda"))
     with pytest.raises(RuntimeError):
         G(torch.randn(2, 64, device="cuda"), torch.randn(2, 256, device="cuda"))
+
+
+def test_generator_input_gradients_fail_loudly():
+    """The tensor-core generator produces parameter gradients only; asking for d/d(noise) or d/d(sentence) raises
+    instead of silently returning zeros, while detached inputs and no_grad calls keep working."""
+    from gan_codes_b200.modules import Generator
+    G = Generator(32, 100).cuda()
+    noise, sent = torch.randn(2, 100, device="cuda"), torch.randn(2, 256, device="cuda")
+    with pytest.raises(RuntimeError, match="not produced"):
+        G(noise.clone().requires_grad_(), sent)
+    with pytest.raises(RuntimeError, match="not produced"):
+        G(noise, sent.clone().requires_grad_())
+    with torch.no_grad():
+        assert G(noise.clone().requires_grad_(), sent).shape == (2, 3, 256, 256)
+    assert G(noise, sent).requires_grad

@@ -71,6 +71,36 @@ def test_oracle_matches_reference_digests(name):
         _close("final/D/" + k, digest(v), gold["final/D/" + k], rtol=tight or 2e-4)
 
 
+def test_oracle_matches_reference_fp64_phase_digests():
+    """tests/golden/native_b2_fp64_phases.npz: the reference's modules in float64 at the native size, the three
+    phases' losses and every gradient from the SAME weights (oracle/make_golden.make_phases).  The oracle reproduces
+    all 337 digests to 1e-9; the GPU tests hold the fp32 tier to 1e-4 and the bf16 path to its tier against them."""
+    gold = np.load(os.path.join(GOLD, "native_b2_fp64_phases.npz"))
+    ws, batch = float(gold["config"][0]), int(gold["config"][1])
+    dt = torch.float64
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    g_sd = O.init_generator_state(32, 100, gamma_range=(0.2, 1.0), dtype=dt)
+    d_sd = O.init_discriminator_state(32, gamma_range=(0.2, 1.0), weight_scale=ws, dtype=dt)
+    images, sent, noise = O.synthetic_batch(batch, 256, dtype=dt)
+    gl, dl = O._leaf(g_sd), O._leaf(d_sd)
+    fake = O.generator_forward(gl, noise, sent)
+    d_loss = O.d_hinge_loss(dl, images, fake.detach(), sent)
+    got = {"phase/d_loss": d_loss, "phase/fake": fake}
+    got.update({"phase/d_grad/" + k: g for k, g in O._grads(d_loss, dl, zero_if_unused=False).items()})
+    probe = {}
+    dl2 = O._leaf(d_sd)
+    gp = O.magp_loss(dl2, images, sent, probe)
+    got.update({"phase/gp_loss": gp, "phase/gp_n": probe["gp_n"], "phase/gp_gx": probe["gp_gx"],
+                "phase/gp_gs": probe["gp_gs"]})
+    got.update({"phase/gp_grad/" + k: g for k, g in O._grads(gp, dl2, zero_if_unused=True).items()})
+    g_loss = O.g_hinge_loss(d_sd, fake, sent)
+    got["phase/g_loss"] = g_loss
+    got.update({"phase/g_grad/" + k: g for k, g in O._grads(g_loss, gl, zero_if_unused=False).items()})
+    assert set(got) == set(gold.files) - {"config"}
+    for k, v in got.items():
+        _close(k, digest(v), gold[k], rtol=1e-9)
+
+
 def test_state_layout_counts():
     """269 generator tensors / 12 240 010 params, 30 discriminator tensors / 19 645 254."""
     g = O.init_generator_state()

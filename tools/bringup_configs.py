@@ -11,8 +11,9 @@ batch 64; configs[4]: generator sampling at batch 256), where the CPU oracle can
                   gradient equals the mean of the 16 chunk gradients (linearity in the batch), and `gp_step` applies
                   exactly one clipped Adam update of it
 
-NOT YET RUN ON A B200 (written after round 1's GPU budget was spent); tests/test_zz_trainer_shell_gpu.py does not
-include these cases until they have been (UNVERIFIED).
+First B200 run: round 2 (profiles/r02_configs_b64_b256.log, all rows green); part of `pytest -m gpu`
+(tests/test_gpu_parity.py::test_full_size_properties).  tools/bringup_parity.py holds the direct comparisons with the
+oracle at the same sizes.
 """
 from __future__ import annotations
 
@@ -93,7 +94,7 @@ def gp_step_b64():
             acc += small.ds.grad
     for c in range(0, 16, 5):                                       # 4 of the 16 chunks on the CPU oracle (~1 s each)
         sl = slice(4 * c, 4 * c + 4)
-        ref_losses.append((c, float(O.magp_loss(O._leaf(d_sd), images[sl], sent[sl]))))
+        ref_losses.append((c, float(O.magp_loss(O._leaf(d_sd), images[sl], sent[sl]).detach())))
     mean4 = sum(losses4) / 16
     ok = _report("loss(64) vs mean of 16 batch-4 losses (rel)", abs(loss64 - mean4) / abs(mean4), 2e-3)
     for c, r in ref_losses:
@@ -112,9 +113,6 @@ def gp_step_b64():
     agree = float((torch.sign(delta[strong]) == -torch.sign(grad64[strong])).float().mean())
     ok &= _report("1 - fraction of strong-gradient elements moving against the gradient", 1.0 - agree, 1e-3)
     return bool(ok)
-
-
-UNVERIFIED = set(CASES)
 
 
 def main(argv):
