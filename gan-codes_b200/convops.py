@@ -39,7 +39,8 @@ TRACK_USAGE = False
 # the per-kernel timing pass of bench.py and by DFGAN_NO_SIDE=1).
 SIDE_ENABLED = _os.environ.get("DFGAN_NO_SIDE", "0") != "1"
 N_SIDE = 3            # streams per pool
-POOL_PHASE, POOL_WGRAD = 0, 1
+POOL_PHASE, POOL_WGRAD, POOL_AUX = 0, 1, 2   # AUX: operand re-packs / gradient fold-backs next to the main chain
+N_POOLS = 3
 _SIDE_STREAMS: dict = {}
 _SIDE_DIRTY: dict = {}
 
@@ -51,8 +52,8 @@ def _dev_key(dev) -> int:
 def _side_streams(dev) -> list:
     key = _dev_key(dev)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [[torch.cuda.Stream(device=dev) for _ in range(N_SIDE)] for _ in range(2)]
-        _SIDE_DIRTY[key] = [[False] * N_SIDE for _ in range(2)]
+        _SIDE_STREAMS[key] = [[torch.cuda.Stream(device=dev) for _ in range(N_SIDE)] for _ in range(N_POOLS)]
+        _SIDE_DIRTY[key] = [[False] * N_SIDE for _ in range(N_POOLS)]
     return _SIDE_STREAMS[key]
 
 
@@ -61,14 +62,26 @@ class side:
     issued so far on the current stream.  The body must not allocate; every tensor it touches must stay alive
     until ``join`` of that pool."""
 
-    def __init__(self, idx: int, dev, pool: int = POOL_WGRAD):
-        self.idx, self.dev, self.pool, self.ctx = idx % N_SIDE, dev, pool, None
+    def __init__(self, idx: int, dev, pool: int = POOL_WGRAD, after_pool=None):
+        """after_pool: the body is ordered after everything issued so far on the side streams of THAT pool instead
+        of after the current stream (a consumer of weight-gradient launches that must not stall the main chain)."""
+        self.idx, self.dev, self.pool, self.ctx, self.after_pool = idx % N_SIDE, dev, pool, None, after_pool
 
     def __enter__(self):
         if not SIDE_ENABLED:
             return self
         s = _side_streams(self.dev)[self.pool][self.idx]
-        s.wait_stream(torch.cuda.current_stream(self.dev))
+        if self.after_pool is None:
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+        else:
+            key = _dev_key(self.dev)
+            waited = False
+            for i, o in enumerate(_SIDE_STREAMS[key][self.after_pool]):
+                if _SIDE_DIRTY[key][self.after_pool][i]:
+                    s.wait_stream(o)
+                    waited = True
+            if not waited:
+                s.wait_stream(torch.cuda.current_stream(self.dev))
         _SIDE_DIRTY[_dev_key(self.dev)][self.pool][self.idx] = True
         self.ctx = torch.cuda.stream(s)
         self.ctx.__enter__()

@@ -11,6 +11,7 @@
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace dfgan {
@@ -61,6 +62,18 @@ struct ConvK {
   float* ws;        // partial tile to ws[pixel][Cout]; conv_splitk_epilogue_kernel applies the fused epilogue afterwards
   int dbg;          // DFGAN_DBG bit mask (conv_halo_kernel only): 1 skip epilogue body, 2 skip MMAs, 4 skip TMA loads,
                     // 8 skip tcgen05.ld -- bottleneck isolation, results are garbage
+  // generic kernel, weight tiles as ONE linear bulk copy per k-iteration from the operand packed as the swizzled
+  // shared-memory image (no per-row TMA cost): b_img != nullptr; byte strides as in Halo2K
+  const uint8_t* b_img;
+  long long w_tap_stride, w_chunk_stride;
+  // generic kernel, on-chip split-K: a thread-block cluster of `cluster` CTAs shares one output tile, CTA r runs
+  // slice r of the (tap, chunk) loop; the fp32 partial tiles are exchanged through distributed shared memory
+  // (CTA r receives columns [r * n_tile / cluster, ...) of every partial into stg[src][row][cols]), summed in rank
+  // order and finished by the fused epilogue -- no global workspace, no second pass.  grid == total_tiles * cluster.
+  int cluster;
+  uint32_t stg_off;   // byte offset of the staging area inside the (1024-aligned) dynamic shared memory
+  uint32_t epi;       // EPI_* feature mask the epilogue loop is instantiated for (EPI_GENERIC: run-time tests)
+  int ltw, lth;       // log2(tiles_w), log2(tiles_h) when both are powers of two, else -1
 };
 
 __device__ __forceinline__ void wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -133,29 +146,67 @@ __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused epilogue, specialised at compile time on its feature set.  The epilogue warps are latency-bound on their own
+// instruction stream (ncu source page, round 2: 384 instructions per 128-pixel tile of a C_out = 32 layer for 32
+// outputs per thread, a third of the samples in instruction-fetch / branch stalls while every feature is a run-time
+// `if (p.x)` on a constant-bank load), so every kernel switches ONCE to a loop instantiated for the launch's feature
+// mask; masks outside the curated list run the EPI_GENERIC instantiation (all features tested at run time).
+enum : uint32_t {
+  EPI_BIAS = 1, EPI_LRELU = 2, EPI_MASK = 4, EPI_AUX = 8, EPI_ADDEND = 16, EPI_OUT = 32, EPI_POST1 = 64, EPI_POST2 = 128,
+  EPI_NCHW = 256, EPI_PHASE = 512, EPI_GENERIC = 0x80000000u
+};
+template <uint32_t F>
+struct Epi {
+  static constexpr bool G = (F & EPI_GENERIC) != 0;
+  __device__ __forceinline__ static bool bias(const ConvK& p) { return G ? p.bias != nullptr : (F & EPI_BIAS) != 0; }
+  __device__ __forceinline__ static bool lrelu(const ConvK& p) { return G ? p.lrelu_pre != 0 : (F & EPI_LRELU) != 0; }
+  __device__ __forceinline__ static bool mask(const ConvK& p) { return G ? p.mask_src != nullptr : (F & EPI_MASK) != 0; }
+  __device__ __forceinline__ static bool aux(const ConvK& p) { return G ? p.aux != nullptr : (F & EPI_AUX) != 0; }
+  __device__ __forceinline__ static bool addend(const ConvK& p) { return G ? p.addend != nullptr : (F & EPI_ADDEND) != 0; }
+  __device__ __forceinline__ static bool out(const ConvK& p) { return G ? p.out != nullptr : (F & EPI_OUT) != 0; }
+  __device__ __forceinline__ static bool post(const ConvK& p) { return G ? p.post_mode != 0 : (F & (EPI_POST1 | EPI_POST2)) != 0; }
+  __device__ __forceinline__ static bool post2(const ConvK& p) { return G ? p.post_mode == 2 : (F & EPI_POST2) != 0; }
+  __device__ __forceinline__ static bool nchw(const ConvK& p) { return G ? p.out_nchw != nullptr : (F & EPI_NCHW) != 0; }
+  __device__ __forceinline__ static bool phase(const ConvK& p) { return G ? p.phase_cout != 0 : (F & EPI_PHASE) != 0; }
+};
+// the masks the two networks launch (tools: DFGAN_DBG=64 prints them); everything else -> EPI_GENERIC
+#define DFGAN_EPI_LIST(X) X(32u) X(33u) X(34u) X(36u) X(48u) X(58u) X(60u) X(137u) X(177u) X(113u) X(560u) X(649u) X(256u) X(257u)
+__host__ __device__ constexpr bool epi_listed(uint32_t f) {
+#define DFGAN_EPI_CMP(V) if (f == V) return true;
+  DFGAN_EPI_LIST(DFGAN_EPI_CMP)
+#undef DFGAN_EPI_CMP
+  return false;
+}
+// EPI_DISPATCH(mask, CALL): CALL(F) expands to the statement run with the compile-time mask F
+#define DFGAN_EPI_CASE_(V) case V: DFGAN_EPI_CALL_(V); break;
+#define EPI_DISPATCH(mask)                    \
+  switch (mask) {                             \
+    DFGAN_EPI_LIST(DFGAN_EPI_CASE_)           \
+    default: DFGAN_EPI_CALL_(EPI_GENERIC); break; \
+  }
+
 // One 16-column chunk of the fused epilogue for one output pixel (see dfgan_conv_run in the header).
 // mask / addend rows of a chunk, requested ahead of use (their DRAM latency was the largest marginal cost of the
 // fused epilogues, tools/prof_epilogue.py): chunk 0 before the accumulator-ready wait, chunk c+1 before chunk c
 struct EpiPre {
   uint4 m0, m1, a0, a1;
 };
-__device__ __forceinline__ void epi_prefetch(const ConvK& p, EpiPre& e, bool on, long long m_off, long long a_off) {
-  if (!on) return;
-  if (p.mask_src) ldg256(p.mask_src + m_off, e.m0, e.m1);
-  if (p.addend) ldg256(p.addend + a_off, e.a0, e.a1);
-}
 // request the mask / addend rows of the chunk at tile column c (output column gcol) for this thread's pixel
+template <uint32_t F>
 __device__ __forceinline__ void epi_pre_issue(const ConvK& p, EpiPre& e, bool valid, int gcol, int c, int n, int h,
                                               int w, long long o_off, long long a_off) {
-  if (!(p.mask_src || p.addend) || !valid || c >= p.n_tile || gcol >= p.Cout) return;
+  if (!(Epi<F>::mask(p) || Epi<F>::addend(p))) return;
+  if (!valid || c >= p.n_tile || gcol >= p.Cout) return;
   int col = gcol;
   long long oo = o_off;
-  if (p.phase_cout) {
+  if (Epi<F>::phase(p)) {
     const int ph = gcol / p.phase_cout;
     col = gcol - ph * p.phase_cout;
     oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
   }
-  epi_prefetch(p, e, true, oo + col, a_off + col);
+  if (Epi<F>::mask(p)) ldg256(p.mask_src + oo + col, e.m0, e.m1);
+  if (Epi<F>::addend(p)) ldg256(p.addend + a_off + col, e.a0, e.a1);
 }
 __device__ __forceinline__ void unpack_bf16x16(const uint4& s0, const uint4& s1, float* v) {
   const uint32_t u[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -163,38 +214,40 @@ __device__ __forceinline__ void unpack_bf16x16(const uint4& s0, const uint4& s1,
   for (int i = 0; i < 8; ++i) unpack_bf16x2(u[i], v[2 * i], v[2 * i + 1]);
 }
 
+template <uint32_t F>
 __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], int col, int n, int h, int w,
                                                long long o_off, long long a_off, float scale, const EpiPre& pre) {
-    if (p.bias) {
+    using E = Epi<F>;
+    if (E::bias(p)) {
       float b[16];
       load_f32x16(p.bias + col, b);
 #pragma unroll
       for (int i = 0; i < 16; i += 2) add2(v[i], v[i + 1], v[i], v[i + 1], b[i], b[i + 1]);
     }
-    if (p.lrelu_pre) {
+    if (E::lrelu(p)) {
 #pragma unroll
       for (int i = 0; i < 16; i += 2) lrelu2(v[i], v[i + 1], p.slope);
     }
-    if (p.mask_src) {
+    if (E::mask(p)) {
       float m[16];
       unpack_bf16x16(pre.m0, pre.m1, m);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] *= (m[i] > 0.f ? 1.f : p.slope);
     }
-    if (p.aux) {
+    if (E::aux(p)) {
       // continue from the stored (bf16) value: what the backward pass reads back is exactly what
       // the rest of the forward used
       store_round_bf16x16(p.aux + o_off + col, v);
     }
 #pragma unroll
     for (int i = 0; i < 16; i += 2) mul2(v[i], v[i + 1], v[i], v[i + 1], scale, scale);
-    if (p.addend) {
+    if (E::addend(p)) {
       float a[16];
       unpack_bf16x16(pre.a0, pre.a1, a);
 #pragma unroll
       for (int i = 0; i < 16; i += 2) fma2(v[i], v[i + 1], a[i], a[i + 1], p.add_scale, p.add_scale, v[i], v[i + 1]);
     }
-    if (p.out_nchw) {
+    if (E::nchw(p)) {
       // image boundary: fp32 planar store, lanes of a warp hold consecutive w -> coalesced
       const long long hw = static_cast<long long>(p.H) * p.W;
       float* dst = p.out_nchw + (static_cast<long long>(n) * p.co_valid) * hw +
@@ -204,18 +257,18 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
         if (col + i < p.co_valid) dst[(col + i) * hw] = p.tanh_out ? tanhf(v[i]) : v[i];
       }
     }
-    if (p.out) {
-      if (p.post_mode) store_round_bf16x16(p.out + o_off + col, v);
+    if (E::out(p)) {
+      if (E::post(p)) store_round_bf16x16(p.out + o_off + col, v);
       else store_bf16x16(p.out + o_off + col, v);
     }
-    if (p.post_mode) {
+    if (E::post(p)) {
       // the follow-up pointwise chain is evaluated on the bf16-rounded value that `out`/`aux`
       // hold, so a backward pass that recomputes it from the stored tensor sees identical masks
-      if (!p.out) {
+      if (!E::out(p)) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = round_bf16(v[i]);
       }
-      if (p.post_mode == 2) {
+      if (E::post2(p)) {
         const long long t_off = static_cast<long long>(n) * p.tab_stride + col;
         float ga[16], ba[16];
         load_f32x16_a32(p.tab_ga + t_off, ga);
@@ -234,6 +287,221 @@ __device__ __forceinline__ void epilogue_chunk(const ConvK& p, float (&v)[16], i
       for (int i = 0; i < 16; i += 2) lrelu2(v[i], v[i + 1], p.slope);
       store_bf16x16(p.out2 + o_off + col, v);
     }
+}
+// chunk at output column `col` of pixel (n, h, w): resolves the output phase of merged-phase launches
+template <uint32_t F>
+__device__ __forceinline__ void epilogue_at(const ConvK& p, float (&v)[16], int col, int n, int h, int w, long long o_off,
+                                            long long a_off, float scale, const EpiPre& pre) {
+  if (Epi<F>::phase(p)) {
+    const int ph = col / p.phase_cout;
+    const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
+    epilogue_chunk<F>(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale, pre);
+  } else {
+    epilogue_chunk<F>(p, v, col, n, h, w, o_off, a_off, scale, pre);
+  }
+}
+
+// tile index -> (tile column, tile row, image) of the 16 x 8 brick grid; powers of two (every layer of the two
+// networks) take the shift / mask path instead of two integer divisions per tile and thread
+__device__ __forceinline__ void brick_coords(const ConvK& p, int mt, int& tw, int& th, int& n) {
+  if (p.ltw >= 0 && p.lth >= 0) {
+    tw = mt & (p.tiles_w - 1);
+    const int r = mt >> p.ltw;
+    th = r & (p.tiles_h - 1);
+    n = r >> p.lth;
+  } else {
+    tw = mt % p.tiles_w;
+    const int r = mt / p.tiles_w;
+    th = r % p.tiles_h;
+    n = r / p.tiles_h;
+  }
+}
+
+// Epilogue loop of the two halo kernels (16 x 8 pixel bricks; thread = pixel): two warpgroups alternate tiles over
+// n_acc TMEM accumulator stages, or (col_split) both work on every tile on alternating 16-column chunks.
+template <uint32_t F>
+__device__ __forceinline__ void brick_epilogue(const ConvK& p, int n_acc, uint64_t* tfull, uint64_t* tempty,
+                                               uint32_t tmem_base, int warp, int lane) {
+  const int group = (warp - 2) >> 2;       // 0 or 1
+  const int q = warp & 3;                   // TMEM lane quadrant this warp may read
+  const int row = q * 32 + lane;
+  const int bw = row & 7, bh = row >> 3;
+  const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+  int acc = 0, i = 0;
+  uint32_t aphase = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
+    if (p.col_split || (i & 1) == group) {
+      int nt = 0, mt = tile;
+      if (p.n_tiles_n > 1) {
+        nt = tile % p.n_tiles_n;
+        mt = tile / p.n_tiles_n;
+      }
+      int tw, th, n;
+      brick_coords(p, mt, tw, th, n);
+      const int w = (tw << 3) + bw, h = (th << 4) + bh;
+      const bool valid = (w < p.W) && (h < p.H);
+      const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+      const long long a_off = Epi<F>::addend(p) ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
+                                                   (w >> p.add_shift) * p.add_sw)
+                                                : 0;
+      const int c0 = p.col_split ? group * 16 : 0, cstep = p.col_split ? 32 : 16;
+      const int colbase = nt * p.n_tile;
+      EpiPre nxt{};
+      epi_pre_issue<F>(p, nxt, valid, colbase + c0, c0, n, h, w, o_off, a_off);
+      wait_bounded(&tfull[acc], aphase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+      for (int c = c0; c < p.n_tile; c += cstep) {
+        const EpiPre cur = nxt;
+        const int col = colbase + c;
+        epi_pre_issue<F>(p, nxt, valid, col + cstep, c + cstep, n, h, w, o_off, a_off);
+        float v[16];
+        if (p.dbg & 8) continue;
+        tmem_ld16(taddr + c, v);
+        if (valid && col < p.Cout && !(p.dbg & 1)) epilogue_at<F>(p, v, col, n, h, w, o_off, a_off, scale, cur);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (++acc == n_acc) {
+      acc = 0;
+      aphase ^= 1;
+    }
+  }
+}
+
+// Epilogue of the generic kernel: thread = pixel row of a BN x BH x BW brick.
+template <uint32_t F>
+__device__ __forceinline__ void generic_epilogue(const ConvK& p, uint8_t* smem, uint64_t* tfull, uint64_t* tempty,
+                                                 uint32_t tmem_base, int warp, int lane) {
+  const int BW = 1 << p.lbw, BH = 1 << p.lbh;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int bw = row & (BW - 1);
+  const int bh = (row >> p.lbw) & (BH - 1);
+  const int bn = row >> (p.lbw + p.lbh);
+  const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
+  if (p.cluster > 1) {
+    // ---- on-chip split-K (one work item per CTA: item == blockIdx.x, slice == cluster rank)
+    const uint32_t S = static_cast<uint32_t>(p.cluster), rank = cluster_ctarank();
+    const int cw = p.n_tile / p.cluster;                    // columns this CTA finishes (multiple of 16)
+    const int tile = static_cast<int>(blockIdx.x) / p.k_splits;
+    const int nt = tile % p.n_tiles_n;
+    int mt = tile / p.n_tiles_n;
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int th = mt % p.tiles_h;
+    const int tn = mt / p.tiles_h;
+    const int w = (tw << p.lbw) + bw, h = (th << p.lbh) + bh;
+    const int n = tn * (128 >> (p.lbw + p.lbh)) + bn;
+    const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+    const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+    const long long a_off = Epi<F>::addend(p) ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh + (w >> p.add_shift) * p.add_sw) : 0;
+    float* stg = reinterpret_cast<float*>(smem + p.stg_off);          // [S][cw / 4][128 rows][4] fp32
+    const int col0 = nt * p.n_tile + static_cast<int>(rank) * cw;      // first output column of this CTA's share
+    EpiPre nxt{};
+    epi_pre_issue<F>(p, nxt, valid, col0, 0, n, h, w, o_off, a_off);
+    wait_bounded(&tfull[0], 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    // staging layout [src][column quad][row][4 floats]: the 32 lanes of a warp (consecutive rows) write / read 512
+    // consecutive bytes per instruction -- conflict-free on both sides of the exchange
+    const int cq = cw >> 2;
+    const uint32_t my_base = smem_u32(stg + (static_cast<size_t>(rank) * cq * 128 + row) * 4);
+    for (uint32_t d = 0; d < S; ++d) {
+      const uint32_t dst = mapa_cluster(my_base, d);
+      for (int c = 0; c < cw; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + d * cw + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          st_cluster_f32x4(dst + static_cast<uint32_t>(((c + i) >> 2) * 128 * 16), v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();
+    for (int c = 0; c < cw; c += 16) {
+      const EpiPre cur = nxt;
+      const int col = col0 + c;
+      epi_pre_issue<F>(p, nxt, valid, col + 16, c + 16 < cw ? 0 : p.n_tile, n, h, w, o_off, a_off);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      for (uint32_t s2 = 0; s2 < S; ++s2) {                  // fixed rank order: the sum is reproducible
+        const float4* src = reinterpret_cast<const float4*>(stg) + (static_cast<size_t>(s2) * cq + (c >> 2)) * 128 + row;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 f = src[i * 128];
+          v[4 * i] += f.x, v[4 * i + 1] += f.y, v[4 * i + 2] += f.z, v[4 * i + 3] += f.w;
+        }
+      }
+      if (valid && col < p.Cout) epilogue_at<F>(p, v, col, n, h, w, o_off, a_off, scale, cur);
+    }
+    return;
+  }
+  int as = 0;
+  uint32_t aphase = 0;
+  for (int item = blockIdx.x; item < p.total_tiles * p.k_splits; item += gridDim.x) {
+    const int tile = item / p.k_splits;
+    const int nt = tile % p.n_tiles_n;
+    int mt = tile / p.n_tiles_n;
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int th = mt % p.tiles_h;
+    const int tn = mt / p.tiles_h;
+    const int w = (tw << p.lbw) + bw, h = (th << p.lbh) + bh;
+    const int n = tn * (128 >> (p.lbw + p.lbh)) + bn;
+    const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
+    const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
+    const long long a_off = Epi<F>::addend(p) ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
+                                                 (w >> p.add_shift) * p.add_sw)
+                                              : 0;
+    if (p.k_splits > 1) {
+      // split-K through global memory: add this slice's partial sums to the fp32 workspace; the fused epilogue runs
+      // in a second pass
+      wait_bounded(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+      float* wrow = p.ws + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.Cout + nt * p.n_tile;
+      for (int c = 0; c < p.n_tile; c += 16) {
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        if (valid && nt * p.n_tile + c < p.Cout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(wrow + c + i, v[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+      continue;
+    }
+    EpiPre nxt{};
+    epi_pre_issue<F>(p, nxt, valid, nt * p.n_tile, 0, n, h, w, o_off, a_off);
+    wait_bounded(&tfull[as], aphase);
+    tc_fence_after();
+    const uint32_t taddr =
+        tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
+    for (int c = 0; c < p.n_tile; c += 16) {
+      const EpiPre cur = nxt;
+      const int col = nt * p.n_tile + c;
+      epi_pre_issue<F>(p, nxt, valid, col + 16, c + 16, n, h, w, o_off, a_off);
+      float v[16];
+      tmem_ld16(taddr + c, v);
+      if (valid && col < p.Cout) epilogue_at<F>(p, v, col, n, h, w, o_off, a_off, scale, cur);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[as]);
+    as ^= 1;
+    if (as == 0) aphase ^= 1;
+  }
 }
 
 template <int BK>
@@ -275,6 +543,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // distributed shared memory may only be touched once every CTA of the cluster has started executing
+  if (p.cluster > 1) cluster_sync_all();
   // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
   // previous kernel; from here on its results are needed.  The successor may start its own prologue right away.
   pdl_wait();
@@ -308,11 +578,21 @@ __global__ void __launch_bounds__(kConvThreads, 1)
         if (leader) {
           mbar_expect_tx(&full[ps.stage], stage_bytes);
           tma_load_4d(sa, ma, &full[ps.stage], c * BK, wx, wy, n0);
-          tma_load_2d(sa + p.a_bytes, &maps.b, &full[ps.stage], c * BK, brow);
+          if (p.b_img)
+            bulk_load(sa + p.a_bytes,
+                      p.b_img + static_cast<long long>(p.tap_wrow[t]) * p.w_tap_stride + c * p.w_chunk_stride +
+                          static_cast<long long>(nt) * p.n_tile * 128,
+                      p.b_bytes, &full[ps.stage]);
+          else
+            tma_load_2d(sa + p.a_bytes, &maps.b, &full[ps.stage], c * BK, brow);
         }
         __syncwarp();
         ps.advance(p.n_stages);
       }
+    }
+    if (p.cluster > 1) {
+      __syncwarp();
+      cluster_sync_all();
     }
   } else if (warp == 1) {
     PipeState ps;
@@ -348,80 +628,14 @@ __global__ void __launch_bounds__(kConvThreads, 1)
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-  } else {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int bw = row & (BW - 1);
-    const int bh = (row >> p.lbw) & (BH - 1);
-    const int bn = row >> (p.lbw + p.lbh);
-    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int item = blockIdx.x; item < p.total_tiles * p.k_splits; item += gridDim.x) {
-      const int tile = item / p.k_splits;
-      const int nt = tile % p.n_tiles_n;
-      int mt = tile / p.n_tiles_n;
-      const int tw = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int tn = mt / p.tiles_h;
-      const int w = (tw << p.lbw) + bw, h = (th << p.lbh) + bh;
-      const int n = tn * (128 >> (p.lbw + p.lbh)) + bn;
-      const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
-      const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
-      const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
-                                          (w >> p.add_shift) * p.add_sw)
-                                       : 0;
-      if (p.k_splits > 1) {
-        // split-K: add this slice's partial sums to the fp32 workspace; the fused epilogue runs in a second pass
-        wait_bounded(&tfull[as], aphase);
-        tc_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
-        float* wrow = p.ws + ((static_cast<long long>(n) * p.H + h) * p.W + w) * p.Cout + nt * p.n_tile;
-        for (int c = 0; c < p.n_tile; c += 16) {
-          float v[16];
-          tmem_ld16(taddr + c, v);
-          if (valid && nt * p.n_tile + c < p.Cout) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(wrow + c + i, v[i]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
-        continue;
-      }
-      EpiPre nxt{};
-      epi_pre_issue(p, nxt, valid, nt * p.n_tile, 0, n, h, w, o_off, a_off);
-      wait_bounded(&tfull[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
-      for (int c = 0; c < p.n_tile; c += 16) {
-        const EpiPre cur = nxt;
-        const int col = nt * p.n_tile + c;
-        epi_pre_issue(p, nxt, valid, col + 16, c + 16, n, h, w, o_off, a_off);
-        float v[16];
-        tmem_ld16(taddr + c, v);
-        if (valid && col < p.Cout) {
-          if (p.phase_cout) {
-            const int ph = col / p.phase_cout;
-            const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-            epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale, cur);
-          } else {
-            epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale, cur);
-          }
-        }
-      }
-      tc_fence_before();
+    if (p.cluster > 1) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      cluster_sync_all();
     }
+  } else {
+#define DFGAN_EPI_CALL_(V) generic_epilogue<V>(p, smem, tfull, tempty, tmem_base, warp, lane)
+    EPI_DISPATCH(p.epi)
+#undef DFGAN_EPI_CALL_
   }
 
   tc_fence_before();
@@ -452,15 +666,8 @@ __global__ void __launch_bounds__(256) conv_splitk_epilogue_kernel(const __grid_
   const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
   const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh + (w >> p.add_shift) * p.add_sw) : 0;
   EpiPre pre{};
-  epi_pre_issue(p, pre, true, c * 16, 0, n, h, w, o_off, a_off);
-  const int gcol = c * 16;
-  if (p.phase_cout) {
-    const int ph = gcol / p.phase_cout;
-    const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-    epilogue_chunk(p, v, gcol - ph * p.phase_cout, n, h, w, oo, a_off, scale, pre);
-  } else {
-    epilogue_chunk(p, v, gcol, n, h, w, o_off, a_off, scale, pre);
-  }
+  epi_pre_issue<EPI_GENERIC>(p, pre, true, c * 16, 0, n, h, w, o_off, a_off);
+  epilogue_at<EPI_GENERIC>(p, v, c * 16, n, h, w, o_off, a_off, scale, pre);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -869,57 +1076,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
       }
     }
   } else {
-    const int group = (warp - 2) >> 2;       // 0 or 1: tiles alternate between the two epilogue warpgroups
-    const int q = warp & 3;                   // TMEM lane quadrant this warp may read
-    const int row = q * 32 + lane;
-    const int bw = row & 7, bh = row >> 3;
-    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
-    int acc = 0, i = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-      if (p.col_split || (i & 1) == group) {
-        const int tw = tile % p.tiles_w;
-        const int r = tile / p.tiles_w;
-        const int th = r % p.tiles_h;
-        const int n = r / p.tiles_h;
-        const int w = (tw << 3) + bw, h = (th << 4) + bh;
-        const bool valid = (w < p.W) && (h < p.H);
-        const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
-        const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
-                                            (w >> p.add_shift) * p.add_sw)
-                                         : 0;
-        const int c0 = p.col_split ? group * 16 : 0, cstep = p.col_split ? 32 : 16;
-        EpiPre nxt{};
-        epi_pre_issue(p, nxt, valid, c0, c0, n, h, w, o_off, a_off);
-        wait_bounded(&tfull[acc], aphase);
-        tc_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-        for (int c = c0; c < p.n_tile; c += cstep) {
-          const EpiPre cur = nxt;
-          epi_pre_issue(p, nxt, valid, c + cstep, c + cstep, n, h, w, o_off, a_off);
-          float v[16];
-          if (p.dbg & 8) continue;
-          tmem_ld16(taddr + c, v);
-          if (valid && !(p.dbg & 1)) {
-            if (p.phase_cout) {
-              const int ph = c / p.phase_cout;
-              const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-              epilogue_chunk(p, v, c - ph * p.phase_cout, n, h, w, oo, a_off, scale, cur);
-            } else {
-              epilogue_chunk(p, v, c, n, h, w, o_off, a_off, scale, cur);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-      }
-      if (++acc == hp.n_acc) {
-        acc = 0;
-        aphase ^= 1;
-      }
-    }
+#define DFGAN_EPI_CALL_(V) brick_epilogue<V>(p, hp.n_acc, tfull, tempty, tmem_base, warp, lane)
+    EPI_DISPATCH(p.epi)
+#undef DFGAN_EPI_CALL_
   }
 
   tc_fence_before();
@@ -1414,56 +1573,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
     }
     __syncwarp();
   } else {
-    const int group = (warp - 2) >> 2;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int bw = row & 7, bh = row >> 3;
-    const float scale = p.scale_imm * (p.scale_dev ? __ldg(p.scale_dev) : 1.f);
-    int acc = 0, i = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++i) {
-      if (p.col_split || (i & 1) == group) {
-        const int nt = tile % p.n_tiles_n;
-        int mt = tile / p.n_tiles_n;
-        const int tw = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int n = mt / p.tiles_h;
-        const int w = (tw << 3) + bw, h = (th << 4) + bh;
-        const bool valid = (w < p.W) && (h < p.H);
-        const long long o_off = n * p.out_sn + h * p.out_sh + w * p.out_sw;
-        const long long a_off = p.addend ? (n * p.add_sn + (h >> p.add_shift) * p.add_sh +
-                                            (w >> p.add_shift) * p.add_sw)
-                                         : 0;
-        const int c0 = p.col_split ? group * 16 : 0, cstep = p.col_split ? 32 : 16;
-        EpiPre nxt{};
-        epi_pre_issue(p, nxt, valid, nt * p.n_tile + c0, c0, n, h, w, o_off, a_off);
-        wait_bounded(&tfull[acc], aphase);
-        tc_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-        for (int c = c0; c < p.n_tile; c += cstep) {
-          const EpiPre cur = nxt;
-          const int col = nt * p.n_tile + c;
-          epi_pre_issue(p, nxt, valid, col + cstep, c + cstep, n, h, w, o_off, a_off);
-          float v[16];
-          tmem_ld16(taddr + c, v);
-          if (valid && col < p.Cout) {
-            if (p.phase_cout) {
-              const int ph = col / p.phase_cout;
-              const long long oo = n * p.out_sn + (2 * h + (ph >> 1)) * p.out_sh + (2 * w + (ph & 1)) * p.out_sw;
-              epilogue_chunk(p, v, col - ph * p.phase_cout, n, h, w, oo, a_off, scale, cur);
-            } else {
-              epilogue_chunk(p, v, col, n, h, w, o_off, a_off, scale, cur);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
-      }
-      if (++acc == hp.n_acc) acc = 0, aphase ^= 1;
-    }
+#define DFGAN_EPI_CALL_(V) brick_epilogue<V>(p, hp.n_acc, tfull, tempty, tmem_base, warp, lane)
+    EPI_DISPATCH(p.epi)
+#undef DFGAN_EPI_CALL_
   }
   tc_fence_before();
   __syncthreads();
@@ -1556,6 +1668,27 @@ static uint32_t pow2_cols(int c) {
 
 using namespace dfgan;
 
+// feature set of a launch's fused epilogue (bit mask, see EPI_* in the kernel section)
+static uint32_t epi_flags_of(const dfgan_conv_desc* d) {
+  uint32_t f = 0;
+  if (d->bias) f |= 1u;
+  if (d->lrelu_pre) f |= 2u;
+  if (d->mask_src) f |= 4u;
+  if (d->aux) f |= 8u;
+  if (d->addend) f |= 16u;
+  if (d->out) f |= 32u;
+  if (d->post_mode == 1) f |= 64u;
+  if (d->post_mode == 2) f |= 128u;
+  if (d->out_nchw) f |= 256u;
+  if (d->phase_cout) f |= 512u;
+  return f;
+}
+static void dbg_print_launch(const char* family, int cin, int geom, const dfgan_conv_desc* d, int n_tile) {
+  static const bool on = getenv("DFGAN_DBG") && (atoi(getenv("DFGAN_DBG")) & 64);
+  if (on)
+    fprintf(stderr, "launch %s cin %d geom %d epi %u | N%d %dx%d Cout%d taps%d n_tile %d add_shift %d tanh %d\n", family, cin,
+            geom, epi_flags_of(d), d->N, d->H, d->W, d->Cout, d->n_taps, n_tile, d->add_shift, d->tanh_out);
+}
 static void fill_epilogue(ConvK& k, const dfgan_conv_desc* d) {
   k.out = static_cast<__nv_bfloat16*>(d->out);
   k.out_sw = d->out_sw, k.out_sh = d->out_sh, k.out_sn = d->out_sn;
@@ -1572,6 +1705,15 @@ static void fill_epilogue(ConvK& k, const dfgan_conv_desc* d) {
   k.tab_stride = d->tab_stride;
   k.out_nchw = d->out_nchw, k.co_valid = d->co_valid, k.tanh_out = d->tanh_out;
   k.phase_cout = d->phase_cout;
+  static const bool epi_generic = getenv("DFGAN_EPI_GENERIC") != nullptr;   // A/B switch: run-time feature tests
+  const uint32_t f = epi_flags_of(d);
+  k.epi = (!epi_generic && epi_listed(f)) ? f : EPI_GENERIC;
+}
+// after tiles_w / tiles_h are known: shift / mask tile decoding when both are powers of two
+static void fill_tile_logs(ConvK& k) {
+  const bool pw = (k.tiles_w & (k.tiles_w - 1)) == 0, ph = (k.tiles_h & (k.tiles_h - 1)) == 0;
+  k.ltw = (pw && ph) ? ilog2(k.tiles_w) : -1;
+  k.lth = (pw && ph) ? ilog2(k.tiles_h) : -1;
 }
 
 // executed work of a launch: real output pixels x Cout x (taps * Cin) MACs; bytes = every source view read once
@@ -1590,7 +1732,21 @@ static double launch_bytes(const dfgan_conv_desc* d) {
 // Generic-kernel tiling: brick geometry, N tile, tile count and the number of K splits an under-filled launch wants.
 struct GenericPlan {
   int lbw, lbh, n_tile, tiles_w, tiles_h, tiles_n, n_tiles_n, total_tiles, k_iters, k_splits;
+  int cluster;    // > 1: on-chip split-K over a thread-block cluster of that many CTAs
+  int b_image;    // weight tiles come from the swizzled-image copy of the operand (one bulk copy per k-iteration)
 };
+// environment switches, read once per process (the same cached value everywhere they are consulted)
+static bool env_off(const char* name) { return getenv(name) != nullptr && atoi(getenv(name)) != 0; }
+static bool halo_disabled() { static const bool v = env_off("DFGAN_NO_HALO"); return v; }
+static bool halo2_disabled() { static const bool v = env_off("DFGAN_NO_HALO2"); return v; }
+// (measured round 2, tools/prof_lowres.py: the bulk-copied weight tile is 5-10 % SLOWER than the tiled load in the
+// generic kernel -- these launches are bound by the ~60 B/cycle one SM can pull in, not by TMA box rows -- so the
+// image path of the generic kernel is opt-in: DFGAN_BIMG=1)
+static bool bimg_disabled() { static const bool v = !env_off("DFGAN_BIMG"); return v; }
+static bool cluster_disabled() { static const bool v = env_off("DFGAN_NO_CLUSTER"); return v; }
+static bool generic_b_image(const dfgan_conv_desc* d) {
+  return !bimg_disabled() && d->wpack_img && d->Cin % 64 == 0 && d->img_rows_per_slot > 0;
+}
 static bool plan_generic(const dfgan_conv_desc* d, GenericPlan& g) {
   brick_geometry(d->W, d->H, g.lbw, g.lbh);
   const int BW = 1 << g.lbw, BH = 1 << g.lbh, BN = 128 / (BW * BH);
@@ -1608,6 +1764,28 @@ static bool plan_generic(const dfgan_conv_desc* d, GenericPlan& g) {
            2 * m_tiles * ((d->Cout + n_tile - 1) / n_tile) < num_sms())
       n_tile /= 2;
   }
+  const int BK0 = (d->Cin % 64 == 0) ? 64 : 32;
+  const int k_iters0 = d->n_taps * (d->Cin / BK0);
+  g.cluster = 1;
+  g.b_image = generic_b_image(d) ? 1 : 0;
+  if (!cluster_disabled() && d->n_tile_hint == 0 && !d->out_nchw && k_iters0 >= 8) {
+    // Low-resolution launches: a handful of output tiles with K loops of 16..128 iterations, each bound by what ONE SM
+    // can pull in (TMA: one box row per ~4.5 cycles; L2 -> SM ~64 B/cycle).  A cluster of S CTAs per tile splits the K
+    // loop S ways and reduces on chip.  N tile <= 128 keeps the fp32 staging area at 64 KB.
+    const long long m_tiles = static_cast<long long>((d->W + BW - 1) / BW) * ((d->H + BH - 1) / BH) *
+                              ((d->N + BN - 1) / BN);
+    int nt_c = d->Cout <= 128 ? d->Cout : 128;
+    if (d->Cout % nt_c == 0 && nt_c % 16 == 0) {
+      const long long tiles_c = m_tiles * (d->Cout / nt_c);
+      static const int sp_max = getenv("DFGAN_CLUSTER_MAX") ? atoi(getenv("DFGAN_CLUSTER_MAX")) : 4;
+      int sp = sp_max;
+      while (sp > 1 && (tiles_c * sp > num_sms() || k_iters0 / sp < 2 || (nt_c / sp) % 16 != 0)) sp >>= 1;
+      if (sp > 1) {
+        n_tile = nt_c;
+        g.cluster = sp;
+      }
+    }
+  }
   if (n_tile > 256 || n_tile % 16 || n_tile > d->Cout) return false;
   g.n_tile = n_tile;
   g.tiles_w = (d->W + BW - 1) / BW;
@@ -1623,6 +1801,10 @@ static bool plan_generic(const dfgan_conv_desc* d, GenericPlan& g) {
   // these launches already overlap with the weight gradients on side streams), so it is opt-in: DFGAN_SPLITK=1.
   static const bool splitk_off = getenv("DFGAN_SPLITK") == nullptr || atoi(getenv("DFGAN_SPLITK")) == 0;
   g.k_splits = 1;
+  if (g.cluster > 1) {
+    g.k_splits = g.cluster;
+    return true;
+  }
   if (!splitk_off && d->n_tile_hint == 0 && !d->out_nchw && 2 * g.total_tiles <= num_sms() && g.k_iters >= 16) {
     int sp = num_sms() / g.total_tiles;
     if (sp > g.k_iters / 8) sp = g.k_iters / 8;
@@ -1635,26 +1817,34 @@ static bool takes_halo_path(const dfgan_conv_desc* d) {
   dfgan_conv_desc ds = *d;   // plan_halo is order-independent in its accept / reject decision
   HaloK hp{};
   int smem = 0;
-  if (getenv("DFGAN_NO_HALO") == nullptr && d->n_tile_hint == 0 && plan_halo(&ds, hp, smem)) return true;
+  if (!halo_disabled() && d->n_tile_hint == 0 && plan_halo(&ds, hp, smem)) return true;
   Halo2K h2{};
   int nt2 = 0;
-  return getenv("DFGAN_NO_HALO2") == nullptr && d->n_tile_hint == 0 && plan_halo2(d, h2, nt2, smem);
+  return !halo2_disabled() && d->n_tile_hint == 0 && plan_halo2(d, h2, nt2, smem);
 }
 extern "C" int64_t dfgan_conv_splitk_bytes(const dfgan_conv_desc* d) {
   if (!d || d->Cin % 32 || d->Cout % 16 || d->N < 1 || d->H < 1 || d->W < 1 || d->n_taps < 1) return 0;
   if (takes_halo_path(d)) return 0;
   GenericPlan g{};
-  if (!plan_generic(d, g) || g.k_splits < 2) return 0;
+  if (!plan_generic(d, g) || g.k_splits < 2 || g.cluster > 1) return 0;   // cluster split-K needs no workspace
   return static_cast<int64_t>(d->N) * d->H * d->W * d->Cout * 4;
 }
 
 // 1 when dfgan_conv_run would take the wide-layer halo kernel (reads wpack_img), 0 when it reads wpack.
 extern "C" int dfgan_conv_uses_image(const dfgan_conv_desc* d) {
   if (!d) return 0;
+  // the narrow-layer halo kernel (C_in <= 64) never has an image; the wide-layer halo kernel and the generic kernel
+  // (weight tiles by bulk copy) both read it whenever one is offered -- the same cached switches as dfgan_conv_run
+  {
+    dfgan_conv_desc ds = *d;
+    HaloK hp{};
+    int smem = 0;
+    if (!halo_disabled() && d->n_tile_hint == 0 && plan_halo(&ds, hp, smem)) return 0;
+  }
   Halo2K h2{};
   int smem2 = 0, nt2 = 0;
-  if (getenv("DFGAN_NO_HALO2") != nullptr || d->n_tile_hint != 0) return 0;
-  return plan_halo2(d, h2, nt2, smem2) ? 1 : 0;
+  if (!halo2_disabled() && d->n_tile_hint == 0 && plan_halo2(d, h2, nt2, smem2)) return 1;
+  return generic_b_image(d) ? 1 : 0;
 }
 
 extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) {
@@ -1681,7 +1871,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   {
     HaloK hp{};
     int smem_halo = 0;
-    static const bool halo_off = getenv("DFGAN_NO_HALO") != nullptr;
+    const bool halo_off = halo_disabled();
     // taps sorted by (source, dy, dx): the sum does not depend on the order, and the standard geometries then have
     // compile-time descriptor offsets (geom_off16)
     dfgan_conv_desc ds = *d;
@@ -1710,6 +1900,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       }
       k.idesc = make_idesc_bf16(128, k.n_tile, 0, 0);
       fill_epilogue(k, d);
+      fill_tile_logs(k);
       for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
         const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
         if (v.C != d->Cin) return DFGAN_E_SHAPE;
@@ -1743,7 +1934,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, GEOM>,                                      \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
-    e = launch_pdl(conv_halo_kernel<CI, GEOM>, grid, kHaloThreads, smem_halo, stream, maps, k, hp);       \
+    e = launch_pdl(conv_halo_kernel<CI, GEOM>, grid, kHaloThreads, smem_halo, stream, 1, maps, k, hp);       \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
   } while (0)
 #define DFGAN_LAUNCH_HALO_C(CI)                                                                           \
@@ -1757,6 +1948,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       default: DFGAN_LAUNCH_HALO(CI, GEOM_RUNTIME); break;                                                \
     }                                                                                                     \
   } while (0)
+      dbg_print_launch("halo", d->Cin, geom, d, k.n_tile);
       if (d->Cin == 64) DFGAN_LAUNCH_HALO_C(64);
       else DFGAN_LAUNCH_HALO_C(32);
 #undef DFGAN_LAUNCH_HALO_C
@@ -1770,7 +1962,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   {
     Halo2K h2{};
     int smem2 = 0, nt2 = 0;
-    static const bool halo2_off = getenv("DFGAN_NO_HALO2") != nullptr;
+    const bool halo2_off = halo2_disabled();
     if (!halo2_off && d->n_tile_hint == 0 && plan_halo2(d, h2, nt2, smem2)) {
       ConvK k{};
       ConvMaps maps{};
@@ -1787,6 +1979,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       }
       k.idesc = make_idesc_bf16(128, k.n_tile, 0, 0);
       fill_epilogue(k, d);
+      fill_tile_logs(k);
       for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
         const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
         if (v.C != d->Cin) return DFGAN_E_SHAPE;
@@ -1800,9 +1993,10 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       const double pix = static_cast<double>(d->N) * d->H * d->W;
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
                         launch_bytes(d), stream);
+      dbg_print_launch("halo2", d->Cin, h2.pair, d, k.n_tile);
       cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
       if (e != cudaSuccess) return static_cast<int>(e);
-      e = launch_pdl(conv_halo2_kernel, grid, kHaloThreads, smem2, stream, maps, k, h2);
+      e = launch_pdl(conv_halo2_kernel, grid, kHaloThreads, smem2, stream, 1, maps, k, h2);
       if (e != cudaSuccess) return static_cast<int>(e);
       count_launch();
       DFGAN_CUDA_CHECK_LAUNCH();
@@ -1821,8 +2015,12 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   k.n_tiles_n = gp.n_tiles_n, k.total_tiles = gp.total_tiles;
   k.n_tile = n_tile;
   k.k_splits = 1;
-  if (gp.k_splits > 1 && d->workspace &&
-      d->ws_bytes >= static_cast<int64_t>(d->N) * d->H * d->W * d->Cout * 4) {
+  k.dbg = getenv("DFGAN_DBG") ? atoi(getenv("DFGAN_DBG")) : 0;
+  k.cluster = gp.cluster;
+  if (gp.cluster > 1) {
+    k.k_splits = gp.cluster;
+  } else if (gp.k_splits > 1 && d->workspace &&
+             d->ws_bytes >= static_cast<int64_t>(d->N) * d->H * d->W * d->Cout * 4) {
     k.k_splits = gp.k_splits;
     k.ws = static_cast<float*>(d->workspace);
   }
@@ -1839,12 +2037,24 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   k.idesc = make_idesc_bf16(128, n_tile, 0, 0);
   k.a_bytes = 128u * BK * 2u;
   k.b_bytes = static_cast<uint32_t>(n_tile) * BK * 2u;
-  int stages = static_cast<int>(kSmemBudget / (k.a_bytes + k.b_bytes));
+  // cluster split-K: [cluster][128][n_tile / cluster] fp32 staging behind the pipeline stages and barriers
+  const size_t stg_bytes = k.cluster > 1 ? static_cast<size_t>(128) * n_tile * 4 : 0;
+  int stages = static_cast<int>((kSmemBudget - stg_bytes) / (k.a_bytes + k.b_bytes));
   if (stages > 8) stages = 8;
+  if (k.cluster > 1) {
+    const int need = (gp.k_iters + k.cluster - 1) / k.cluster;   // a slice never has more iterations in flight
+    if (stages > need) stages = need < 2 ? 2 : need;
+  }
   if (stages < 2) return DFGAN_E_SHAPE;
   k.n_stages = stages;
   k.tmem_cols = pow2_cols(2 * n_tile);
   fill_epilogue(k, d);
+  if (gp.b_image && BK == 64) {
+    // image layout [slot][chunk][rows_per_slot][64] (dfgan_pack_weights image=1); a tap's wrow counts rows
+    k.b_img = static_cast<const uint8_t*>(d->wpack_img);
+    k.w_chunk_stride = static_cast<long long>(d->img_rows_per_slot) * 128;
+    k.w_tap_stride = static_cast<long long>(d->Cin / 64) * 128;
+  }
 
   for (int s = 0; s < DFGAN_MAX_SRC; ++s) {
     const dfgan_view4& v = d->src[s < d->n_src ? s : 0];
@@ -1855,29 +2065,37 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
   int rc = make_map_2d(&maps.b, d->wpack, d->w_rows, d->Cin, BK, n_tile);
   if (rc) return rc;
 
-  const size_t smem = static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 1024 + 256;
+  // stages | barriers + TMEM slot (256 B) | staging (16-byte aligned) ; +1024 for the in-kernel alignment
+  k.stg_off = static_cast<uint32_t>(static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 256);
+  const size_t smem = static_cast<size_t>(stages) * (k.a_bytes + k.b_bytes) + 1024 + 256 + stg_bytes;
   int grid = k.total_tiles * k.k_splits;
   const int cap = d->max_ctas > 0 ? d->max_ctas : num_sms();
-  if (grid > cap) grid = cap;
+  if (grid > cap && k.cluster <= 1) grid = cap;       // a cluster launch is one CTA per work item
+  if (k.dbg & 32)
+    fprintf(stderr, "generic: N%d %dx%d Cin%d Cout%d taps%d | n_tile %d tiles %d k_iters %d k_splits %d cluster %d stages %d "
+            "a %u b %u stg_off %u smem %zu grid %d bimg %p\n", d->N, d->H, d->W, d->Cin, d->Cout, d->n_taps, n_tile,
+            k.total_tiles, gp.k_iters, k.k_splits, k.cluster, stages, k.a_bytes, k.b_bytes, k.stg_off, smem, grid,
+            (const void*)k.b_img);
   const double pix = static_cast<double>(d->N) * d->H * d->W;
   ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
                     launch_bytes(d), stream);
+  dbg_print_launch("generic", d->Cin, k.cluster, d, n_tile);
   cudaError_t e;
   if (BK == 64) {
     e = cudaFuncSetAttribute(conv_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    e = launch_pdl(conv_umma_kernel<64>, grid, kConvThreads, smem, stream, maps, k);
+    e = launch_pdl(conv_umma_kernel<64>, grid, kConvThreads, smem, stream, k.cluster, maps, k);
     if (e != cudaSuccess) return static_cast<int>(e);
   } else {
     e = cudaFuncSetAttribute(conv_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
-    e = launch_pdl(conv_umma_kernel<32>, grid, kConvThreads, smem, stream, maps, k);
+    e = launch_pdl(conv_umma_kernel<32>, grid, kConvThreads, smem, stream, k.cluster, maps, k);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   count_launch();
-  if (k.k_splits > 1) {
+  if (k.k_splits > 1 && k.cluster <= 1) {
     const long long total = static_cast<long long>(d->N) * d->H * d->W * (d->Cout / 16);
     conv_splitk_epilogue_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(k);
     count_launch();
@@ -1927,7 +2145,7 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
     cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<CI, CO>,                                       \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
-    e = launch_pdl(wgrad_halo_kernel<CI, CO>, grid, kConvThreads, smem_halo, stream, maps, hk);           \
+    e = launch_pdl(wgrad_halo_kernel<CI, CO>, grid, kConvThreads, smem_halo, stream, 1, maps, hk);           \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
   } while (0)
       if (d->Cin == 32 && d->Cout == 32) DFGAN_LAUNCH_WHALO(32, 32);
@@ -2023,7 +2241,7 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  e = launch_pdl(wgrad_umma_kernel, grid, kConvThreads, smem, stream, maps, k);
+  e = launch_pdl(wgrad_umma_kernel, grid, kConvThreads, smem, stream, 1, maps, k);
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   DFGAN_CUDA_CHECK_LAUNCH();

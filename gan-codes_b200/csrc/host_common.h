@@ -43,14 +43,25 @@ int make_map_2d(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int
 // Launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait() before it touches
 // global memory).  DFGAN_NO_PDL=1 falls back to plain stream-ordered launches.
 bool pdl_enabled();
+// cluster > 1 additionally launches thread-block clusters of that many CTAs along x (grid must be a multiple of it).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int cluster,
+                              Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = static_cast<unsigned>(cluster), at[n].val.clusterDim.y = 1, at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at, cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -396,15 +396,30 @@ __global__ void __launch_bounds__(256) sqnorm_det_kernel(const float* __restrict
                                                          float* scratch) {
   __shared__ float red[8];
   __shared__ bool last;
-  float acc = 0.f;
-  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 4; i < n; i += gridDim.x * 1024LL) {
+  // four independent 16-byte loads in flight per thread and iteration; every partial sum is formed in a fixed order,
+  // so the result does not depend on scheduling
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const long long stride = gridDim.x * 1024LL;
+  long long i = (blockIdx.x * 256LL + threadIdx.x) * 4;
+  for (; i + 3 * stride + 3 < n; i += 4 * stride) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(g + i));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(g + i + stride));
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(g + i + 2 * stride));
+    const float4 v3 = __ldg(reinterpret_cast<const float4*>(g + i + 3 * stride));
+    a0 += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+    a1 += v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+    a2 += v2.x * v2.x + v2.y * v2.y + v2.z * v2.z + v2.w * v2.w;
+    a3 += v3.x * v3.x + v3.y * v3.y + v3.z * v3.z + v3.w * v3.w;
+  }
+  for (; i < n; i += stride) {
     if (i + 3 < n) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(g + i));
-      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      a0 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     } else {
-      for (long long j = i; j < n; ++j) acc += g[j] * g[j];
+      for (long long j = i; j < n; ++j) a0 += g[j] * g[j];
     }
   }
+  float acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -412,18 +427,28 @@ __global__ void __launch_bounds__(256) sqnorm_det_kernel(const float* __restrict
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + gridDim.x);
   if (threadIdx.x == 0) {
     float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += red[i];
+    for (int k = 0; k < 8; ++k) s += red[k];
     scratch[blockIdx.x] = s;
     __threadfence();
     last = atomicAdd(counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {
+    // the last block folds the per-block partials: strided per-thread sums, then the same fixed tree as above
     __threadfence();
     float s = 0.f;
-    for (unsigned int i = 0; i < gridDim.x; ++i) s += __ldcg(scratch + i);
-    *out += s;
-    *counter = 0u;
+    for (unsigned int k = threadIdx.x; k < gridDim.x; k += 256) s += __ldcg(scratch + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += red[k];
+      *out += t;
+      *counter = 0u;
+    }
   }
 }
 __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* out) {
@@ -623,7 +648,7 @@ int dfgan_sqnorm(const float* g, int64_t n, float* out, dfgan_stream_t st) {
 int dfgan_sqnorm_det(const float* g, int64_t n, float* out, float* scratch, int scratch_floats, dfgan_stream_t st) {
   if (!g || !out || !scratch || n < 1 || (reinterpret_cast<uintptr_t>(g) & 15)) return DFGAN_E_ARG;
   long long blocks = (n + 1023) / 1024;
-  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();   // 4 x 148 blocks x 4 loads in flight per thread
   if (scratch_floats < blocks + 1) return DFGAN_E_ARG;
   sqnorm_det_kernel<<<static_cast<int>(blocks), 256, 0, STREAM(st)>>>(g, n, out, scratch);
   count_launch();

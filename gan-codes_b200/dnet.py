@@ -19,6 +19,10 @@ from . import kernels as K
 BF16, F32 = torch.bfloat16, torch.float32
 SENT_DIM = 256
 MERGE_MAX = 64   # see gnet.MERGE_MAX
+LATE_BLOCKS = 3  # blocks (from the end of the trunk) whose operands are re-packed by the deferred table
+import os as _os
+DEFER_PACK = _os.environ.get("DFGAN_NO_DEFER_PACK", "0") != "1"     # A/B switches for the two side-stream placements
+EARLY_FLUSH = _os.environ.get("DFGAN_NO_EARLY_FLUSH", "0") != "1"
 
 
 def d_plan(params: Dict[str, torch.Tensor]) -> List[tuple]:
@@ -69,10 +73,17 @@ class DPacked:
         self.refresh(params)
 
     def _build(self, params: Dict[str, torch.Tensor]) -> None:
-        pp = K.PackPlan(params["img_forward.0.weight"].device)
+        """Two re-pack tables: `_pp` (stem and the high-resolution blocks: few parameters, consumed first) and
+        `_pp_late` (the last LATE_BLOCKS blocks and the head: > 90 % of the parameters, first consumed several hundred
+        microseconds into a forward sweep) -- the trainer runs the second one next to the start of the next sweep."""
+        dev = params["img_forward.0.weight"].device
+        early, late = K.PackPlan(dev), K.PackPlan(dev)
+        self.first_late = max(len(self.plan) - LATE_BLOCKS, 0)
+        pp = early
         pp.add(params["img_forward.0.weight"], self.w0_f, as_matrix=True, cols_pad=32)
         pp.add(params["img_forward.0.weight"], self.w0_d, transpose=True, rows_pad=16)
-        for (p, cin, cout, sc), b in zip(self.plan, self.blocks):
+        for i, ((p, cin, cout, sc), b) in enumerate(zip(self.plan, self.blocks)):
+            pp = late if i >= self.first_late else early
             w4, w3 = params[p + ".residual_conv.0.weight"], params[p + ".residual_conv.2.weight"]
             pp.add_with_image(w4, b["w4_f"])
             if cin <= MERGE_MAX:
@@ -84,17 +95,37 @@ class DPacked:
             if sc:
                 pp.add(params[p + ".scale_conv.weight"], b["ws_f"], scale=0.25)
                 pp.add(params[p + ".scale_conv.weight"], b["ws_d"], transpose=True)
+        pp = late
         pp.add(params["img_sentence_forward.0.weight"], self.wh_f)
         pp.add(params["img_sentence_forward.0.weight"], self.wh_d, transpose=True)
-        self._pp = pp
+        self._pp, self._pp_late = early, late
+        self._late_pending = False
 
-    def refresh(self, params: Dict[str, torch.Tensor]) -> None:
-        """Re-pack every GEMM operand from the fp32 master weights: one kernel launch."""
+    def refresh(self, params: Dict[str, torch.Tensor], defer_late: bool = False) -> None:
+        """Re-pack every GEMM operand from the fp32 master weights: two kernel launches.  defer_late: the second
+        (large) table runs on a side stream; every consumer of a late operand calls `sync_late` first."""
         ptrs = tuple(t.data_ptr() for t in params.values())
         if ptrs != self._ptrs:
             self._build(params)
             self._ptrs = ptrs
+        self.sync_late()
         self._pp.run()
+        if defer_late and co.SIDE_ENABLED and DEFER_PACK:
+            dev = params["img_forward.0.weight"].device
+            with co.side(0, dev, co.POOL_AUX):
+                self._pp_late.run()
+            self._late_pending = True
+        else:
+            self._pp_late.run()
+
+    def sync_late(self) -> None:
+        if self._late_pending:
+            self._late_pending = False
+            co.join(self._pp_late.device, co.POOL_AUX)
+
+    def prune(self, used: set) -> None:
+        self._pp.prune(used)
+        self._pp_late.prune(used)
 
 
 def _oihw_strides(w: torch.Tensor) -> tuple:
@@ -122,7 +153,9 @@ def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = 
     x = e(n, h, w, pk.n_c)
     co.conv_run([xcol], co.taps_1x1(), pk.w0_f, pk.n_c, x, bias=params["img_forward.0.bias"])
     saved = []
-    for (p, cin, cout, sc), b in zip(pk.plan, pk.blocks):
+    for i, ((p, cin, cout, sc), b) in enumerate(zip(pk.plan, pk.blocks)):
+        if i == pk.first_late:
+            pk.sync_late()
         h, w = h // 2, w // 2
         pv = co.parity_views(x)
         s = e(n, h, w, cout)
@@ -148,12 +181,14 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
     accumulator (None = skip all parameter gradients, i.e. the G step / the first GP sweep).  cots (optional
     dict) receives the cotangent at every conv output for the MA-GP second sweep.  Returns d/d(image) as fp32
     NCHW when need_gx."""
+    pk.sync_late()
     dev = g_emb.device
     n = ctx["n"]
     e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
     g_y = g_emb
     kept = []     # also keeps every tensor a side stream reads alive until the join below
     n_side = 0
+    flushed: set = set()
     for (p, cin, cout, sc), b, (x, c1, r) in zip(reversed(pk.plan), reversed(pk.blocks), reversed(ctx["saved"])):
         h, w = c1.shape[1], c1.shape[2]
         g_c2 = e(n, h, w, cout)
@@ -197,6 +232,14 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
             n_side += 2
         kept.append((g_y, g_c2, g_c1, g_s))
         g_y = g_x
+        if EARLY_FLUSH and grads is not None and len(kept) == len(pk.plan) - pk.first_late and pk.first_late > 0:
+            # the low-resolution blocks hold > 90 % of the weights: fold their gradients back (tap-major scratch ->
+            # OIHW) as soon as their weight-gradient launches are queued, on a side stream next to the rest of the sweep
+            late_names = [nm for (p_, _, _, _) in pk.plan[pk.first_late:]
+                          for nm in (p_ + ".residual_conv.0.weight", p_ + ".residual_conv.2.weight")]
+            with co.side(1, dev, co.POOL_AUX, after_pool=co.POOL_WGRAD):
+                pk.ws.flush(grads, late_names)
+            flushed = set(late_names)
     if grads is not None:
         with co.side(n_side, dev):
             co.wgrad_run([ctx["xcol"]], [(0, 0, 0, 0)], g_y, grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
@@ -210,7 +253,8 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
         co.conv_run([g_y], co.taps_3x3_dgrad(16), pk.w0_d, 16, None, out_nchw=gx, co_valid=3)
     co.join(dev)
     if grads is not None:
-        pk.ws.flush(grads, [n for n in pk.ws.shapes if n.startswith("img_forward.")])
+        co.join(dev, co.POOL_AUX)
+        pk.ws.flush(grads, [n for n in pk.ws.shapes if n.startswith("img_forward.") and n not in flushed])
     return gx
 
 
@@ -221,6 +265,7 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
     cotangent at its output) into grads -- exactly the parameter gradient of <tangent, d logits/d image>
     (aten::_convolution_double_backward at deep_fusion_gan/model.py:207 without the zero-gradient waste).
     Bias gradients stay zero (gotcha G3).  Returns the tangent of the embeds (NHWC bf16)."""
+    pk.sync_late()
     n, _, h, w = t_img.shape
     dev = t_img.device
     e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
@@ -268,6 +313,7 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
 def head_forward(pk: DPacked, params, embed: torch.Tensor, sent: torch.Tensor, ctx: Optional[dict] = None,
                  sscale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """discriminator/model.py:43-59.  embed fp32 NCHW [b,16*n_c,4,4], sent fp32 [b,256] -> logits fp32 [b]."""
+    pk.sync_late()
     if embed.dim() != 4 or tuple(embed.shape[2:]) != (4, 4) or sent.shape[-1] != SENT_DIM or \
             embed.shape[1] + SENT_DIM != pk.ccat or sent.shape[0] != embed.shape[0]:
         raise RuntimeError(f"Sizes of tensors must match: embed {tuple(embed.shape)} / sentence "
@@ -288,6 +334,7 @@ def head_forward(pk: DPacked, params, embed: torch.Tensor, sent: torch.Tensor, c
 def head_backward(pk: DPacked, params, ctx: dict, g_logit: Optional[torch.Tensor], grads: Optional[dict],
                   need_sent: bool, cots: Optional[dict] = None):
     """g_logit fp32 [b] (None = ones).  Returns (g_embed fp32 NCHW, g_sent fp32 [b,256] or None)."""
+    pk.sync_late()
     b, cat, hid = ctx["b"], ctx["cat"], ctx["hid"]
     dev = cat.device
     w2 = params["img_sentence_forward.2.weight"]
@@ -313,6 +360,7 @@ def head_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_embed: torch.Tens
                  sscale: Optional[torch.Tensor], grads: dict) -> torch.Tensor:
     """Tangent sweep of the head (second half of App. C-3).  t_embed fp32 NCHW, t_sent fp32 [b,256] (scaled per
     sample by sscale).  Accumulates the two head weight gradients, returns the tangent logits fp32 [b]."""
+    pk.sync_late()
     b, hid = ctx["b"], ctx["hid"]
     dev = hid.device
     t_cat = torch.empty_like(ctx["cat"])

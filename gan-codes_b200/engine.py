@@ -28,6 +28,9 @@ from . import kernels as K
 
 F32, BF16 = torch.float32, torch.bfloat16
 STAGE_MIXED = os.environ.get("DFGAN_STAGE_MIXED", "0") == "1"
+# world > 1: capture the NCCL all-reduces inside the iteration's CUDA graph (one replay per iteration); "0" falls back
+# to four graph segments with eager all-reduces in between
+DP_ONE_GRAPH = os.environ.get("DFGAN_DP_ONE_GRAPH", "1") == "1"
 
 
 class FlatState:
@@ -160,7 +163,8 @@ class DFGANTrainer:
 
     def _d_update(self):
         self.ds.apply(self.world)
-        self.dpk.refresh(self.ds.params)
+        # the large (low-resolution) operands are re-packed next to the start of the following forward sweep
+        self.dpk.refresh(self.ds.params, defer_late=True)
 
     def _g_update(self):
         self.gs.apply(self.world)
@@ -241,11 +245,17 @@ class DFGANTrainer:
         self._seg_out = {}
         segs = self._segments(*self._in)
         torch.cuda.synchronize()
-        if self.world == 1:
+        if self.world == 1 or DP_ONE_GRAPH:
+            # data parallel: the three NCCL all-reduces are captured too (ProcessGroupNCCL supports stream capture
+            # once the communicator exists -- the eager warm-up iterations created it), so N ranks replay ONE graph
+            # per iteration exactly like one rank does.  thread_local: the NCCL watchdog thread may touch the CUDA
+            # API while this thread captures.
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for fn, _ in segs:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                for fn, st in segs:
                     fn()
+                    if st is not None:
+                        st.reduce(self.world)
             self._graphs = [(g, None)]
         else:
             self._graphs = []
@@ -340,7 +350,7 @@ class DFGANTrainer:
             self.last = self._run_eager(*self._in)
             if first:
                 co.TRACK_USAGE = False
-                self.dpk._pp.prune(co.USED)
+                self.dpk.prune(co.USED)
                 self.gpk._pp.prune(co.USED)
             return self.last
         if self._graph is None:
@@ -360,6 +370,7 @@ class DFGANTrainer:
         loss = self._gp_step(images.to(dev, F32).contiguous(), sentence_embeds.to(dev, F32).contiguous())
         self.ds.reduce(self.world)
         self._d_update()
+        self.dpk.sync_late()
         return loss
 
     @torch.no_grad()

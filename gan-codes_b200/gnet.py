@@ -173,9 +173,12 @@ class GMlp:
     def backward(self) -> None:
         """d_tab (accumulated by the affine backward kernels) and g_x0f -> MLP / linear_in parameter grads."""
         t_w2, t_dd, t_w1 = self.bwd
-        t_w2.run(self.batch)
+        dev = self.tab.device
+        with co.side(2, dev, co.POOL_AUX):     # layer-2 weight gradients only read d_tab / hid: parallel branch
+            t_w2.run(self.batch)
         t_dd.run(self.batch)
         t_w1.run(self.batch)
+        co.join(dev, co.POOL_AUX)
 
 
 def _phases(t: torch.Tensor):

@@ -4,8 +4,10 @@ batch 64; configs[4]: generator sampling at batch 256), where the CPU oracle can
     python tools/bringup_configs.py [case ...]
 
     sample_b256   every image of a 256-image `trainer.sample` batch equals the image the same (noise, sentence) row gets
-                  in a 4-image batch (the forward has no cross-sample term and no split accumulation: bit-exact), and
-                  the first 4 match the fp32 oracle to the bf16 tolerance
+                  in a 4-image batch (the forward has no cross-sample term; since round 2 the low-resolution layers of
+                  the SMALL batch split their K loops over a thread-block cluster, so the fp32 partial sums are formed
+                  in a different order and bf16-stored activations differ in the last bit: 1e-2 on the [-1, 1] image
+                  instead of bit-exact), and the first 4 match the fp32 oracle to the bf16 tolerance
     gp_step_b64   MA-GP at batch 64: the loss is the mean of the per-sample penalties, so it equals the mean over 16
                   chunks of 4 of the batch-4 program's loss (four of which are checked against the ORACLE); the flat
                   gradient equals the mean of the 16 chunk gradients (linearity in the batch), and `gp_step` applies
@@ -65,7 +67,7 @@ def sample_b256():
     for lo in (0, 124, 252):
         part = big.sample(noise[lo:lo + 4].cuda(), sent[lo:lo + 4].cuda())       # batch-4 program, same weights
         worst = max(worst, float((part - out[lo:lo + 4]).abs().max()))
-    ok &= _report("rows of the 256-batch vs the same rows as a 4-batch (max abs)", worst, 1e-30)
+    ok &= _report("rows of the 256-batch vs the same rows as a 4-batch (max abs)", worst, 1e-2)
     with torch.no_grad():
         ref = O.generator_forward(g_sd, noise[:4], sent[:4])
     err = float((out[:4].cpu() - ref).norm() / ref.norm())
@@ -96,11 +98,12 @@ def gp_step_b64():
         sl = slice(4 * c, 4 * c + 4)
         ref_losses.append((c, float(O.magp_loss(O._leaf(d_sd), images[sl], sent[sl]).detach())))
     mean4 = sum(losses4) / 16
-    ok = _report("loss(64) vs mean of 16 batch-4 losses (rel)", abs(loss64 - mean4) / abs(mean4), 2e-3)
+    # (different K-loop splits at batch 4 and batch 64: bf16 last-bit differences, amplified by n^6 / n^4)
+    ok = _report("loss(64) vs mean of 16 batch-4 losses (rel)", abs(loss64 - mean4) / abs(mean4), 1e-2)
     for c, r in ref_losses:
         ok &= _report(f"chunk {c}: batch-4 loss vs fp32 oracle (rel)", abs(losses4[c] - r) / abs(r), 1e-1)
     ok &= _report("grad(64) vs mean of 16 chunk gradients (rel L2)",
-                  float((grad64 - acc / 16).norm() / (acc / 16).norm()), 5e-3)
+                  float((grad64 - acc / 16).norm() / (acc / 16).norm()), 2e-2)
     # (3) gp_step = exactly one clipped Adam update with that gradient: |delta| <= lr / sqrt(1 - beta2) element-wise,
     #     sign(delta) = -sign(grad) wherever the gradient is not rounding noise, step counter 1
     before = big.ds.flat.clone()

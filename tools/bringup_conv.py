@@ -253,6 +253,54 @@ def halo2():
 
 
 @case
+def lowres():
+    """Low-resolution grids (4x4, 8x8) through the generic kernel's two round-2 paths: weight tiles bulk-copied from the
+    swizzled image, and on-chip split-K over a thread-block cluster with the partial tiles reduced through distributed
+    shared memory -- plain and with every fused epilogue, against torch and against the single-CTA path (n_tile hint
+    switches the cluster off)."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co
+    ok = True
+    for (N, C, Kc, H) in [(32, 512, 512, 4), (5, 256, 256, 4), (32, 256, 256, 8), (7, 512, 128, 8), (32, 768, 64, 4),
+                          (3, 128, 256, 8)]:
+        x = torch.randn(N, C, H, H, device="cuda").bfloat16()
+        w = (torch.randn(Kc, C, 3, 3, device="cuda") / (3 * C ** 0.5)).bfloat16()
+        b = torch.randn(Kc, device="cuda")
+        ref = F.conv2d(x.float(), w.float(), b, padding=1)
+        xn = _nhwc(x)
+        wp, keep = _pack_img(w)
+        o1, o2 = (torch.empty(N, H, H, Kc, device="cuda", dtype=torch.bfloat16) for _ in range(2))
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o1, bias=b)
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o2, bias=b, n_tile=min(Kc, 128))
+        # fused epilogue on the cluster path: D conv3 (lrelu, aux, gate, addend) and the masked data gradient
+        gamma = torch.tensor([0.37], device="cuda")
+        add = torch.randn(N, H, H, Kc, device="cuda").bfloat16()
+        msk = torch.randn(N, H, H, Kc, device="cuda").bfloat16()
+        o3, aux = (torch.empty(N, H, H, Kc, device="cuda", dtype=torch.bfloat16) for _ in range(2))
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o3, lrelu_pre=True, aux=aux, scale_dev=gamma, addend=add)
+        r3 = F.leaky_relu(F.conv2d(x.float(), w.float(), None, padding=1), 0.2)
+        ref3 = 0.37 * r3.bfloat16().float() + add.float().permute(0, 3, 1, 2)
+        o4 = torch.empty(N, H, H, Kc, device="cuda", dtype=torch.bfloat16)
+        co.conv_run([xn], co.taps_3x3(Kc), wp, Kc, o4, mask_src=msk)
+        ref4 = F.conv2d(x.float(), w.float(), None, padding=1) * torch.where(msk.float() > 0, 1.0, 0.2).permute(0, 3, 1, 2)
+        # 4x4 stride 2 onto this grid (16 taps over four parity views of a 2H x 2H input)
+        x2 = torch.randn(N, C, 2 * H, 2 * H, device="cuda").bfloat16()
+        w4 = (torch.randn(Kc, C, 4, 4, device="cuda") / (4 * C ** 0.5)).bfloat16()
+        r5 = F.leaky_relu(F.conv2d(x2.float(), w4.float(), None, stride=2, padding=1), 0.2)
+        w4p, keep4 = _pack_img(w4)
+        o5 = torch.empty(N, H, H, Kc, device="cuda", dtype=torch.bfloat16)
+        co.conv_run(co.parity_views(_nhwc(x2)), co.taps_4x4s2(Kc), w4p, Kc, o5, lrelu_pre=True)
+        torch.cuda.synchronize()
+        e = [_rel(o1.permute(0, 3, 1, 2), ref), _rel(o1, o2), _rel(o3.permute(0, 3, 1, 2), ref3),
+             _rel(aux.permute(0, 3, 1, 2), r3), _rel(o4.permute(0, 3, 1, 2), ref4), _rel(o5.permute(0, 3, 1, 2), r5)]
+        print(f"lowres N{N} C{C} K{Kc} {H}: 3x3 {e[0]:.3e} vs single-CTA {e[1]:.3e} | D conv3 {e[2]:.3e} aux {e[3]:.3e} "
+              f"| masked {e[4]:.3e} | 4x4s2 {e[5]:.3e}")
+        ok &= e[0] < 8e-3 and e[1] < 2e-3 and max(e[2:]) < 8e-3
+    return ok
+
+
+@case
 def merged():
     """Merged-phase launches: upsample->conv3x3 forward and the 4x4/stride-2 data gradient as ONE conv over 9 shifts."""
     torch = _setup()
