@@ -42,6 +42,7 @@ _TABLE: dict = {
     "dfgan_dres_bwd": [P, P, P, P, P, P, I, I, I, P],
     "dfgan_dot": [P, P, L, P, F, P],
     "dfgan_im2col3": [P, P, P, I, I, I, P],
+    "dfgan_stem_fwd": [P, P, P, P, P, P, I, I, I, P],
     "dfgan_tanh_bwd_pack": [P, P, P, P, I, I, P],
     "dfgan_nchw_to_nhwc": [P, P, I, I, I, P],
     "dfgan_nhwc_to_nchw": [P, P, I, I, I, I, P],

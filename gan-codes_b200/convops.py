@@ -29,6 +29,15 @@ IMAGE_OF: dict = {}
 # its first eager iteration and then drops the never-used copies from the per-step re-pack)
 USED: set = set()
 TRACK_USAGE = False
+# data_ptrs of operand copies a PackPlan.prune() stopped refreshing: consuming one of them is an error (stale weights)
+PRUNED: set = set()
+
+
+def check_not_pruned(t: torch.Tensor, what: str) -> None:
+    if PRUNED and t.data_ptr() in PRUNED:
+        raise RuntimeError(f"{what}: this packed weight copy is no longer re-packed after optimiser steps (it was not "
+                           "consumed by the trainer's first iteration and PackPlan.prune dropped it); a launch that "
+                           "reads it would see stale weights")
 
 
 # ------------------------------------------------------------------------------------ side streams
@@ -233,6 +242,9 @@ def conv_run(srcs: Sequence[torch.Tensor], taps: Sequence[tuple], wpack: torch.T
     if TRACK_USAGE:
         uses_img = img is not None and _lib.lib().dfgan_conv_uses_image(C.byref(d)) == 1
         USED.add(img[0].data_ptr() if uses_img else wpack.data_ptr())
+    elif PRUNED and (wpack.data_ptr() in PRUNED or (img is not None and img[0].data_ptr() in PRUNED)):
+        uses_img = img is not None and _lib.lib().dfgan_conv_uses_image(C.byref(d)) == 1
+        check_not_pruned(img[0] if uses_img else wpack, "conv_run")
     if n * h * w <= SPLITK_MAX_PIXELS:
         # low-resolution launch: offer a zeroed fp32 scratch so the C side can split the K loop over the idle SMs.
         # One persistent scratch per stream (launches on a stream are serialised; the second pass of a split launch

@@ -1689,6 +1689,18 @@ static void dbg_print_launch(const char* family, int cin, int geom, const dfgan_
     fprintf(stderr, "launch %s cin %d geom %d epi %u | N%d %dx%d Cout%d taps%d n_tile %d add_shift %d tanh %d\n", family, cin,
             geom, epi_flags_of(d), d->N, d->H, d->W, d->Cout, d->n_taps, n_tile, d->add_shift, d->tanh_out);
 }
+// per-launch label for the profile dump (host_common: DFGAN_PROFILE_DUMP)
+struct LaunchLabel {
+  char s[120];
+  LaunchLabel(const char* family, int variant, const dfgan_conv_desc* d, int n_tile, int grid) {
+    snprintf(s, sizeof(s), "%s/%d N%d %dx%d Cin%d Cout%d taps%d src%d epi%u ntile%d grid%d", family, variant, d->N, d->H,
+             d->W, d->Cin, d->Cout, d->n_taps, d->n_src, epi_flags_of(d), n_tile, grid);
+  }
+  LaunchLabel(const char* family, const dfgan_wgrad_desc* d, int ks, int grid) {
+    snprintf(s, sizeof(s), "%s N%d %dx%d Cin%d Cout%d taps%d src%d ks%d grid%d", family, d->g.N, d->g.H, d->g.W, d->Cin,
+             d->Cout, d->n_taps, d->n_src, ks, grid);
+  }
+};
 static void fill_epilogue(ConvK& k, const dfgan_conv_desc* d) {
   k.out = static_cast<__nv_bfloat16*>(d->out);
   k.out_sw = d->out_sw, k.out_sh = d->out_sh, k.out_sn = d->out_sn;
@@ -1927,8 +1939,9 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
         }
       }
       const double pix = static_cast<double>(d->N) * d->H * d->W;
+      const LaunchLabel lab("halo", geom, d, k.n_tile, grid);
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
-                        launch_bytes(d), stream);
+                        launch_bytes(d), stream, lab.s);
 #define DFGAN_LAUNCH_HALO(CI, GEOM)                                                                       \
   do {                                                                                                    \
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, GEOM>,                                      \
@@ -1991,8 +2004,9 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
       if (grid > cap) grid = cap;
       k.col_split = (k.total_tiles <= 3 * grid) ? 1 : 0;
       const double pix = static_cast<double>(d->N) * d->H * d->W;
+      const LaunchLabel lab("halo2", h2.pair, d, k.n_tile, grid);
       ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
-                        launch_bytes(d), stream);
+                        launch_bytes(d), stream, lab.s);
       dbg_print_launch("halo2", d->Cin, h2.pair, d, k.n_tile);
       cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
       if (e != cudaSuccess) return static_cast<int>(e);
@@ -2077,8 +2091,9 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
             k.total_tiles, gp.k_iters, k.k_splits, k.cluster, stages, k.a_bytes, k.b_bytes, k.stg_off, smem, grid,
             (const void*)k.b_img);
   const double pix = static_cast<double>(d->N) * d->H * d->W;
+  const LaunchLabel lab("generic", k.cluster, d, n_tile, grid);
   ProfileScope prof(0, 2.0 * pix * d->Cout * d->n_taps * d->Cin * (d->phase_cout ? 16.0 / 36.0 : 1.0),
-                    launch_bytes(d), stream);
+                    launch_bytes(d), stream, lab.s);
   dbg_print_launch("generic", d->Cin, k.cluster, d, n_tile);
   cudaError_t e;
   if (BK == 64) {
@@ -2139,7 +2154,8 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
       double bytes = 2.0 * pix * d->Cout + 4.0 * d->n_taps * d->Cin * d->Cout;
       for (int s = 0; s < d->n_src; ++s)
         bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
-      ProfileScope prof(1, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream);
+      const LaunchLabel lab("wgrad_halo", d, 0, grid);
+      ProfileScope prof(1, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream, lab.s);
 #define DFGAN_LAUNCH_WHALO(CI, CO)                                                                        \
   do {                                                                                                    \
     cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<CI, CO>,                                       \
@@ -2237,7 +2253,8 @@ extern "C" int dfgan_wgrad_run(const dfgan_wgrad_desc* d, dfgan_stream_t stream_
   double bytes = 2.0 * pix * d->Cout + 4.0 * d->n_taps * d->Cin * d->Cout;
   for (int s = 0; s < d->n_src; ++s)
     bytes += 2.0 * d->src[s].N * d->src[s].H * d->src[s].W * d->src[s].C;
-  ProfileScope prof(1, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream);
+  const LaunchLabel lab("wgrad_umma", d, ks, grid);
+  ProfileScope prof(1, 2.0 * pix * d->Cout * d->n_taps * d->Cin, bytes, stream, lab.s);
   cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -1,5 +1,6 @@
 #include "host_common.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -91,16 +92,19 @@ struct ProfRec {
   cudaEvent_t e0, e1;
   int engine;
   double flops, bytes;
+  char label[120];
 };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
-ProfileScope::ProfileScope(int engine, double flops, double bytes, cudaStream_t st_) : slot(-1), st(st_) {
+ProfileScope::ProfileScope(int engine, double flops, double bytes, cudaStream_t st_, const char* label)
+    : slot(-1), st(st_) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r{};
   r.engine = engine, r.flops = flops, r.bytes = bytes;
+  snprintf(r.label, sizeof(r.label), "%s", label ? label : "");
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
   cudaEventRecord(r.e0, st);
   g_prof.push_back(r);
@@ -127,15 +131,20 @@ int dfgan_profile_read(double* out) {
   if (e != cudaSuccess) return static_cast<int>(e);
   std::lock_guard<std::mutex> lk(dfgan::g_prof_mu);
   for (int i = 0; i < 8; ++i) out[i] = 0.0;
+  // per-launch records (tools/prof_perlaunch.py): engine, label, ms, flops, algorithmic bytes
+  const char* dump = getenv("DFGAN_PROFILE_DUMP");
+  FILE* fd = dump ? fopen(dump, "a") : nullptr;
   for (auto& r : dfgan::g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
       double* o = out + (r.engine ? 4 : 0);
       o[0] += ms, o[1] += r.flops, o[2] += r.bytes, o[3] += 1.0;
+      if (fd) fprintf(fd, "%d\t%s\t%.4f\t%.0f\t%.0f\n", r.engine, r.label, ms, r.flops, r.bytes);
     }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
+  if (fd) fclose(fd);
   dfgan::g_prof.clear();
   return DFGAN_OK;
 }

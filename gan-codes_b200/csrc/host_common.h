@@ -16,7 +16,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 // Optional per-launch timing of the two GEMM engines (bench.py's roofline leg): when enabled, every
 // dfgan_conv_run / dfgan_wgrad_run launch is bracketed by a CUDA event pair on its own stream.
 struct ProfileScope {
-  ProfileScope(int engine, double flops, double bytes, cudaStream_t st);
+  // label (optional): kernel family + shape, written per launch by dfgan_profile_read when DFGAN_PROFILE_DUMP=<file>
+  ProfileScope(int engine, double flops, double bytes, cudaStream_t st, const char* label = nullptr);
   ~ProfileScope();
   int slot;
   cudaStream_t st;

@@ -23,6 +23,7 @@ LATE_BLOCKS = 3  # blocks (from the end of the trunk) whose operands are re-pack
 import os as _os
 DEFER_PACK = _os.environ.get("DFGAN_NO_DEFER_PACK", "0") != "1"     # A/B switches for the two side-stream placements
 EARLY_FLUSH = _os.environ.get("DFGAN_NO_EARLY_FLUSH", "0") != "1"
+FUSED_STEM = _os.environ.get("DFGAN_NO_FUSED_STEM", "0") != "1"    # A/B: round-1 pair im2col3 + 1x1 GEMM
 
 
 def d_plan(params: Dict[str, torch.Tensor]) -> List[tuple]:
@@ -128,6 +129,14 @@ class DPacked:
         self._pp_late.prune(used)
 
 
+def _use_operand(t: torch.Tensor, what: str) -> None:
+    """Packed operands consumed outside convops.conv_run take part in the same usage tracking / pruning protocol."""
+    if co.TRACK_USAGE:
+        co.USED.add(t.data_ptr())
+    else:
+        co.check_not_pruned(t, what)
+
+
 def _oihw_strides(w: torch.Tensor) -> tuple:
     co_, ci, kh, kw = w.shape
     return (ci * kh * kw, kh * kw, 1)
@@ -141,17 +150,25 @@ def _check_image(img: torch.Tensor, n_blocks: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ trunk
-def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = None) -> torch.Tensor:
+def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = None,
+                  need_xcol: bool = True) -> torch.Tensor:
     """discriminator/model.py:36-41.  img: fp32 NCHW [N,3,H,H] -> embeds NHWC bf16 [N,4,4,16*n_c].
-    ctx (optional dict) receives the activations the backward / tangent sweeps need."""
+    ctx (optional dict) receives the activations the backward / tangent sweeps need; need_xcol=False skips the
+    im2col tensor of the stem (only its weight gradient reads it: a backward with grads=None never does)."""
     _check_image(img, len(pk.plan))
     n, _, h, w = img.shape
     dev = img.device
     e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
-    xcol = e(n, h, w, 32)
-    K.im2col3(img, xcol)
+    xcol = e(n, h, w, 32) if (ctx is not None and need_xcol) else None
     x = e(n, h, w, pk.n_c)
-    co.conv_run([xcol], co.taps_1x1(), pk.w0_f, pk.n_c, x, bias=params["img_forward.0.bias"])
+    if FUSED_STEM:
+        _use_operand(pk.w0_f, "stem_fwd")
+        K.stem_fwd(img, pk.w0_f, x, bias=params["img_forward.0.bias"], xcol=xcol)
+    else:
+        if xcol is None:
+            xcol = e(n, h, w, 32)
+        K.im2col3(img, xcol)
+        co.conv_run([xcol], co.taps_1x1(), pk.w0_f, pk.n_c, x, bias=params["img_forward.0.bias"])
     saved = []
     for i, ((p, cin, cout, sc), b) in enumerate(zip(pk.plan, pk.blocks)):
         if i == pk.first_late:
@@ -241,6 +258,9 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
                 pk.ws.flush(grads, late_names)
             flushed = set(late_names)
     if grads is not None:
+        if ctx["xcol"] is None:
+            raise RuntimeError("trunk_backward: parameter gradients need the stem im2col tensor "
+                               "(trunk_forward(..., need_xcol=True))")
         with co.side(n_side, dev):
             co.wgrad_run([ctx["xcol"]], [(0, 0, 0, 0)], g_y, grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)
         K.pool(g_y, None, shift=0, colsum=grads["img_forward.0.bias"])
@@ -270,9 +290,13 @@ def trunk_tangent(pk: DPacked, params, ctx: dict, cots: dict, t_img: torch.Tenso
     dev = t_img.device
     e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
     tcol = e(n, h, w, 32)
-    K.im2col3(t_img, tcol, rowscale=rowscale)
     t_x = e(n, h, w, pk.n_c)
-    co.conv_run([tcol], co.taps_1x1(), pk.w0_f, pk.n_c, t_x)
+    if FUSED_STEM:
+        _use_operand(pk.w0_f, "stem_fwd")
+        K.stem_fwd(t_img, pk.w0_f, t_x, rowscale=rowscale, xcol=tcol)
+    else:
+        K.im2col3(t_img, tcol, rowscale=rowscale)
+        co.conv_run([tcol], co.taps_1x1(), pk.w0_f, pk.n_c, t_x)
     # every weight gradient only consumes the tangent chain: side streams, joined at the end of the sweep
     with co.side(0, dev):
         co.wgrad_run([tcol], [(0, 0, 0, 0)], cots["x0"], grads["img_forward.0.weight"], (27, 1, 0), ci_valid=27)

@@ -28,9 +28,11 @@ from . import kernels as K
 
 F32, BF16 = torch.float32, torch.bfloat16
 STAGE_MIXED = os.environ.get("DFGAN_STAGE_MIXED", "0") == "1"
-# world > 1: capture the NCCL all-reduces inside the iteration's CUDA graph (one replay per iteration); "0" falls back
-# to four graph segments with eager all-reduces in between
-DP_ONE_GRAPH = os.environ.get("DFGAN_DP_ONE_GRAPH", "1") == "1"
+# world > 1: "1" captures the NCCL all-reduces inside the iteration's CUDA graph (one replay per iteration).  Measured on
+# 2 B200s (round 2): the iteration is NOT faster (11.56 ms against 11.48 ms with segments) and the process then hangs in
+# dist.barrier() / destroy_process_group() at teardown, so the default stays four graph segments with eager all-reduces
+# in between.
+DP_ONE_GRAPH = os.environ.get("DFGAN_DP_ONE_GRAPH", "0") == "1"
 
 
 class FlatState:
@@ -174,7 +176,7 @@ class DFGANTrainer:
         b = self.batch
         dp, dpk = self.ds.params, self.dpk
         tctx, hctx, cots = {}, {}, {}
-        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, images, tctx))
+        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, images, tctx, need_xcol=False))
         dnet.head_forward(dpk, dp, emb, sent, hctx)
         g_embed, g_sent = dnet.head_backward(dpk, dp, hctx, None, None, True, cots)
         gx = dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_embed), None, True, cots)
@@ -196,7 +198,7 @@ class DFGANTrainer:
         dp, dpk = self.ds.params, self.dpk
         fake = self.g_ctx["img"]
         tctx, hctx = {}, {}
-        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, fake, tctx))
+        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, fake, tctx, need_xcol=False))
         lg = dnet.head_forward(dpk, dp, emb, sent, hctx)
         loss = -lg.mean()
         if self.text_image_loss:

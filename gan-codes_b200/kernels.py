@@ -78,6 +78,18 @@ def im2col3(img, out, rowscale=None):
     _call("dfgan_im2col3", _p(img), _p(rowscale), _p(out), n, h, w, _s())
 
 
+def stem_fwd(img, w0_f, out, bias=None, rowscale=None, xcol=None):
+    """Fused discriminator stem (discriminator/model.py:13): fp32 NCHW image -> NHWC bf16 [N,H,W,32] in one kernel;
+    xcol (optional, NHWC bf16 [N,H,W,32]) additionally receives the im2col tensor the stem's weight gradient reads."""
+    assert img.is_cuda and img.dtype == F32 and img.is_contiguous() and img.shape[1] == 3
+    n, _, h, w = img.shape
+    assert tuple(_nhwc(out)) == (n, h, w, 32) and w0_f.dtype == BF16 and tuple(w0_f.shape) == (32, 32)
+    assert w0_f.is_contiguous() and (bias is None or (bias.dtype == F32 and bias.numel() == 32))
+    if xcol is not None:
+        assert tuple(_nhwc(xcol)) == (n, h, w, 32)
+    _call("dfgan_stem_fwd", _p(img), _p(rowscale), _p(w0_f), _p(bias), _p(out), _p(xcol), n, h, w, _s())
+
+
 def tanh_bwd_pack(g_img, img, out, dbias=None):
     assert g_img.dtype == F32 and img.dtype == F32 and g_img.is_contiguous() and img.is_contiguous()
     n, _, h, w = img.shape
@@ -198,6 +210,7 @@ class PackPlan:
             image=False):
         assert w.dtype == F32 and w.is_contiguous() and out.dtype == BF16 and out.is_contiguous()
         from . import convops
+        convops.PRUNED.discard(out.data_ptr())   # a re-used address starts a new life
         convops.IMAGE_OF.pop(out.data_ptr(), None)   # a re-used address must not inherit a stale image
         co, ci, kh, kw = w.shape
         if as_matrix:
@@ -225,10 +238,13 @@ class PackPlan:
         """Drop the entries whose output operand is not in `used` (data_ptrs); returns how many were dropped.
         block_start of the kept entries is rewritten in place (last 4 bytes of an entry)."""
         import struct
+        from . import convops
         keep = [i for i, o in enumerate(self.outs) if o in used]
         dropped = len(self.outs) - len(keep)
         if dropped == 0 or not keep:
             return 0
+        # a later launch that would consume a dropped (no longer refreshed) copy fails loudly in convops.conv_run
+        convops.PRUNED.update(o for o in self.outs if o not in used)
         entries, start = [], 0
         for i in keep:
             e = bytearray(self.entries[i])

@@ -165,6 +165,13 @@ int dfgan_dot(const void* a, const void* b, int64_t n, float* out, float scale, 
 /* Stem im2col: NCHW fp32 image [N,3,H,W] (optionally scaled per sample) -> NHWC bf16 [N,H,W,32], channel
  * ci*9+r*3+s = img[ci][h+r-1][w+s-1].  replaces: the input gather of nn.Conv2d(3,n_c,3,1,1), discriminator/model.py:13 */
 int dfgan_im2col3(const float* img, const float* rowscale, void* out, int N, int H, int W, dfgan_stream_t st);
+/* Fused stem: out[n,h,w,co] = bf16( bias[co] + sum_k bf16(rowscale[n] * img[n,ci,h+r-1,w+s-1]) * w[co][k] ), k = ci*9+r*3+s,
+ * out NHWC bf16 [N,H,W,32]; w = packed bf16 [32][32] (rows C_out, K padded 27 -> 32 with zeros); bias, rowscale and
+ * xcol optional.  xcol != NULL additionally writes the im2col tensor of dfgan_im2col3 (operand of the stem's weight
+ * gradient).  One kernel: im2col tile built in shared memory, tcgen05.mma, per-pixel epilogue.
+ * replaces: nn.Conv2d(3, n_c, 3, 1, 1) forward, discriminator/model.py:13 (called from build_embeds, :36-41) */
+int dfgan_stem_fwd(const float* img, const float* rowscale, const void* w, const float* bias, void* out, void* xcol,
+                   int N, int H, int W, dfgan_stream_t st);
 /* g_t = g_img*(1-img^2) packed NHWC bf16 [N,HW,32] (3 real channels); dbias[0..2] += sum.  replaces: tanh backward, generator/model.py:29 */
 int dfgan_tanh_bwd_pack(const float* g_img, const float* img, void* out, float* dbias, int N, int HW,
                         dfgan_stream_t st);

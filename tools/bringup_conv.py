@@ -390,6 +390,44 @@ def edge():
 
 
 @case
+def stem():
+    """fused stem kernel (csrc/stem.cu) vs torch fp32 conv2d on the bf16-rounded operands, vs the round-1 pair
+    im2col3 + 1x1 GEMM (bit-identical im2col tensor, outputs equal to the last bf16 bit up to fp32 summation order),
+    with / without bias, per-sample scale, im2col side output; sizes with a ragged last 128-pixel tile."""
+    torch = _setup()
+    import torch.nn.functional as F
+    from gan_codes_b200 import convops as co, kernels as K
+    ok = True
+    for (N, H, W, use_bias, use_scale, want_col) in [(2, 64, 64, True, False, True), (3, 256, 256, True, False, False),
+                                                     (2, 40, 24, False, True, True), (1, 8, 8, True, True, True),
+                                                     (5, 12, 20, True, False, False)]:
+        img = torch.randn(N, 3, H, W, device="cuda")
+        w = torch.randn(32, 3, 3, 3, device="cuda") / 5
+        b = torch.randn(32, device="cuda") if use_bias else None
+        rs = (torch.rand(N, device="cuda") + 0.5) if use_scale else None
+        w0f = torch.empty(32, 32, device="cuda", dtype=torch.bfloat16)
+        K.pack_weights(w, w0f, as_matrix=True, cols_pad=32)
+        out = torch.empty(N, H, W, 32, device="cuda", dtype=torch.bfloat16)
+        col = torch.full((N, H, W, 32), 7.0, device="cuda", dtype=torch.bfloat16) if want_col else None
+        K.stem_fwd(img, w0f, out, bias=b, rowscale=rs, xcol=col)
+        # the pair it replaces
+        col2 = torch.empty(N, H, W, 32, device="cuda", dtype=torch.bfloat16)
+        K.im2col3(img, col2, rowscale=rs)
+        out2 = torch.empty_like(out)
+        co.conv_run([col2], co.taps_1x1(), w0f, 32, out2, bias=b)
+        torch.cuda.synchronize()
+        xs = img if rs is None else img * rs.view(N, 1, 1, 1)
+        ref = F.conv2d(xs.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+        e_ref = _rel(out.permute(0, 3, 1, 2), ref)
+        e_pair = float((out.float() - out2.float()).abs().max() / (out2.float().abs().max() + 1e-30))
+        col_same = True if col is None else bool(torch.equal(col, col2))
+        print(f"stem N{N} {H}x{W} bias {use_bias} scale {use_scale}: vs torch {e_ref:.3e}, vs im2col+GEMM pair "
+              f"{e_pair:.3e}, im2col side output identical: {col_same}")
+        ok &= e_ref < 4e-3 and e_pair < 8e-3 and col_same
+    return ok
+
+
+@case
 def pointwise():
     torch = _setup()
     import torch.nn.functional as F
