@@ -301,6 +301,54 @@ __device__ __forceinline__ void epilogue_at(const ConvK& p, float (&v)[16], int 
   }
 }
 
+// Prefetch depth of the mask / addend rows (16-column chunks requested ahead of use).  The epilogue warps are bound by
+// the latency of these loads, not by their instruction stream (round 2: with ONE chunk in flight per thread a
+// C_out = 64 dgrad + mask launch sat at 3700 cycles per 128-pixel tile = 4 chunks x ~one DRAM latency, 53 % of the HBM
+// roofline, nothing saturated in ncu): all chunks of a tile (up to kEpiDepth) are requested BEFORE the accumulator
+// wait, so the latency is exposed once per tile and overlaps the MMAs of that tile.  Register budget: 8 registers per
+// tensor and chunk; launches that read both tensors keep two chunks in flight.
+template <uint32_t F>
+struct EpiDepth {
+  static constexpr bool both = Epi<F>::G || ((F & EPI_MASK) && (F & EPI_ADDEND));
+  static constexpr bool any = Epi<F>::G || (F & (EPI_MASK | EPI_ADDEND));
+  static constexpr int D = any ? (both ? 2 : 4) : 1;
+};
+// requests chunks c0, c0 + cstep, ... (D of them) of a tile whose columns are [0, n_cols) at output column colbase + c
+template <uint32_t F>
+__device__ __forceinline__ void epi_prefetch_head(const ConvK& p, EpiPre (&pre)[EpiDepth<F>::D], bool valid, int colbase,
+                                                  int c0, int cstep, int n_cols, int n, int h, int w, long long o_off,
+                                                  long long a_off) {
+  constexpr int D = EpiDepth<F>::D;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const int c = c0 + j * cstep;
+    epi_pre_issue<F>(p, pre[j], valid, colbase + c, c < n_cols ? 0 : p.n_tile, n, h, w, o_off, a_off);
+  }
+}
+// processes the chunks of a tile from TMEM address taddr (+ column), refilling the prefetch ring as it goes
+template <uint32_t F>
+__device__ __forceinline__ void epi_process_tile(const ConvK& p, EpiPre (&pre)[EpiDepth<F>::D], uint32_t taddr, bool valid,
+                                                 int colbase, int c0, int cstep, int n_cols, int n, int h, int w,
+                                                 long long o_off, long long a_off, float scale) {
+  constexpr int D = EpiDepth<F>::D;
+  for (int cb = c0; cb < n_cols; cb += D * cstep) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const int c = cb + j * cstep;
+      if (c < n_cols) {
+        const int col = colbase + c;
+        float v[16];
+        if (!(p.dbg & 8)) {
+          tmem_ld16(taddr + c, v);
+          if (valid && col < p.Cout && !(p.dbg & 1)) epilogue_at<F>(p, v, col, n, h, w, o_off, a_off, scale, pre[j]);
+        }
+        const int cn = c + D * cstep;
+        epi_pre_issue<F>(p, pre[j], valid, colbase + cn, cn < n_cols ? 0 : p.n_tile, n, h, w, o_off, a_off);
+      }
+    }
+  }
+}
+
 // tile index -> (tile column, tile row, image) of the 16 x 8 brick grid; powers of two (every layer of the two
 // networks) take the shift / mask path instead of two integer divisions per tile and thread
 __device__ __forceinline__ void brick_coords(const ConvK& p, int mt, int& tw, int& th, int& n) {
@@ -346,21 +394,13 @@ __device__ __forceinline__ void brick_epilogue(const ConvK& p, int n_acc, uint64
                                                 : 0;
       const int c0 = p.col_split ? group * 16 : 0, cstep = p.col_split ? 32 : 16;
       const int colbase = nt * p.n_tile;
-      EpiPre nxt{};
-      epi_pre_issue<F>(p, nxt, valid, colbase + c0, c0, n, h, w, o_off, a_off);
+      EpiPre pre[EpiDepth<F>::D];
+      epi_prefetch_head<F>(p, pre, valid, colbase, c0, cstep, p.n_tile, n, h, w, o_off, a_off);
       wait_bounded(&tfull[acc], aphase);
       tc_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-      for (int c = c0; c < p.n_tile; c += cstep) {
-        const EpiPre cur = nxt;
-        const int col = colbase + c;
-        epi_pre_issue<F>(p, nxt, valid, col + cstep, c + cstep, n, h, w, o_off, a_off);
-        float v[16];
-        if (p.dbg & 8) continue;
-        tmem_ld16(taddr + c, v);
-        if (valid && col < p.Cout && !(p.dbg & 1)) epilogue_at<F>(p, v, col, n, h, w, o_off, a_off, scale, cur);
-      }
+      epi_process_tile<F>(p, pre, taddr, valid, colbase, c0, cstep, p.n_tile, n, h, w, o_off, a_off, scale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -482,20 +522,13 @@ __device__ __forceinline__ void generic_epilogue(const ConvK& p, uint8_t* smem, 
       if (as == 0) aphase ^= 1;
       continue;
     }
-    EpiPre nxt{};
-    epi_pre_issue<F>(p, nxt, valid, nt * p.n_tile, 0, n, h, w, o_off, a_off);
+    EpiPre pre[EpiDepth<F>::D];
+    epi_prefetch_head<F>(p, pre, valid, nt * p.n_tile, 0, 16, p.n_tile, n, h, w, o_off, a_off);
     wait_bounded(&tfull[as], aphase);
     tc_fence_after();
     const uint32_t taddr =
         tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
-    for (int c = 0; c < p.n_tile; c += 16) {
-      const EpiPre cur = nxt;
-      const int col = nt * p.n_tile + c;
-      epi_pre_issue<F>(p, nxt, valid, col + 16, c + 16, n, h, w, o_off, a_off);
-      float v[16];
-      tmem_ld16(taddr + c, v);
-      if (valid && col < p.Cout) epilogue_at<F>(p, v, col, n, h, w, o_off, a_off, scale, cur);
-    }
+    epi_process_tile<F>(p, pre, taddr, valid, nt * p.n_tile, 0, 16, p.n_tile, n, h, w, o_off, a_off, scale);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty[as]);
@@ -880,9 +913,15 @@ constexpr size_t kSmemBudget = 200 * 1024;
 //           descriptor's base-offset field
 //   mode 2: one halo tile, row pitch 8 + halo: arbitrary row shifts, base-offset field per tap         (180 rows)
 // All taps of the packed weight matrix stay resident in shared memory for the life of the CTA.
-// Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 two epilogue warpgroups alternating tiles over
+// Roles: warp 0 TMA producer, warps 1 and 10 MMA issuers (alternate tiles), warps 2..9 two epilogue warpgroups alternating tiles over
 // up to four TMEM accumulator stages.
 constexpr int kHaloThreads = 320;
+// conv_halo_kernel runs a SECOND MMA-issuing warp (warp 10): tcgen05.mma issue is effectively synchronous with the
+// tensor pipe (tools/ubench/mma_pattern.cu: every cycle the issuing thread spends between two tiles -- barrier waits,
+// fences, descriptor set-up, commits; ~700 cycles in this kernel -- is a cycle the pipe idles: 2450 instead of 1750
+// cycles per 36-MMA tile), and two warps that alternate tiles hide each other's gaps completely.  Tiles have their
+// own accumulators, so the two issue streams need no ordering between them.
+constexpr int kHaloNarrowThreads = 352;
 
 // Tap geometries whose A-descriptor offsets are compile-time constants (taps sorted by source, dy, dx).  The MMA
 // issue loop is bound by moving descriptor words from vector to uniform registers (R2UR, ~20 cycles each, 11 per tap
@@ -924,7 +963,7 @@ __device__ __forceinline__ uint64_t with_base_offset(uint64_t desc, uint32_t sad
 }
 
 template <int CIN, int GEOM>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(kHaloNarrowThreads, 1)
     conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvK p,
                      const __grid_constant__ HaloK hp) {
   extern __shared__ uint8_t smem_raw[];
@@ -1014,58 +1053,64 @@ __global__ void __launch_bounds__(kHaloThreads, 1)
         phase ^= 1;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     constexpr uint32_t swz = (CIN == 64) ? SWZ_128B : SWZ_64B;
     constexpr uint32_t sbo_b = 8u * kRowBytes;
     const uint32_t sbo_a = static_cast<uint32_t>(hp.pitch) * kRowBytes;
+    // Two issuing warps alternate tiles (see kHaloNarrowThreads); both walk the whole tile sequence so that the
+    // stage / accumulator counters stay those of the single-issuer loop.
     // Everything the MMA needs (descriptors, TMEM address) is computed by the WHOLE warp so that it is
     // warp-uniform and lives in uniform registers; only the tcgen05 instructions themselves sit under the
     // elected-lane predicate.  (Computing descriptors inside `if (lane == 0)` makes the compiler wrap every
     // UTCHMMA in an ELECT/R2UR waterfall loop -- ~150 cycles per MMA, the former bound of this kernel.)
-    int stage = 0, acc = 0;
+    const int mine = (warp == 1) ? 0 : 1;
+    int stage = 0, acc = 0, it = 0;
     uint32_t phase = 0, aphase = 0;
     wait_bounded(bfull, 0);
     const uint64_t bdesc0 = make_smem_desc(smem_u32(sB), 16, sbo_b, swz);
     const uint64_t b_step16 = hp.b_tap_bytes >> 4;
     const bool leader = elect_one();
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      wait_bounded(&tempty[acc], aphase ^ 1);
-      wait_bounded(&full[stage], phase);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-      const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * a_stage_bytes);
-      // The issue loop must stay a handful of uniform-datapath instructions per MMA (an N=32 MMA is ~40 cycles,
-      // tools/ubench/mma_cost.cu): tap offsets come precomputed from the host, the tap loop is unrolled at
-      // compile time (NT) so they are constant-bank immediates.
-      const uint64_t adesc0 = make_smem_desc(a_base, 16, sbo_a, swz);
-      if (leader && !(p.dbg & 2)) {
-        // ONE elected-lane region for the whole tile; the two bases pass through an empty asm so that nothing
-        // derived from them is hoisted out of the tile loop into vector registers (each use would cost two R2UR)
-        uint64_t ad0 = adesc0, bd0 = bdesc0;
-        asm volatile("" : "+l"(ad0), "+l"(bd0));
-        constexpr int NT = geom_taps(GEOM);
-        if (NT > 0) {
+    const bool dual = !(p.dbg & 16);     // DFGAN_DBG bit 16: single issuing warp (A/B measurement)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if (dual ? ((it & 1) == mine) : (mine == 0)) {
+        wait_bounded(&tempty[acc], aphase ^ 1);
+        wait_bounded(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        const uint32_t a_base = smem_u32(sA + static_cast<size_t>(stage) * a_stage_bytes);
+        // The issue loop must stay a handful of uniform-datapath instructions per MMA (an N=32 MMA is ~40 cycles,
+        // tools/ubench/mma_cost.cu): tap offsets come precomputed from the host, the tap loop is unrolled at
+        // compile time (NT) so they are constant-bank immediates.
+        const uint64_t adesc0 = make_smem_desc(a_base, 16, sbo_a, swz);
+        if (leader && !(p.dbg & 2)) {
+          // ONE elected-lane region for the whole tile; the two bases pass through an empty asm so that nothing
+          // derived from them is hoisted out of the tile loop into vector registers (each use would cost two R2UR)
+          uint64_t ad0 = adesc0, bd0 = bdesc0;
+          asm volatile("" : "+l"(ad0), "+l"(bd0));
+          constexpr int NT = geom_taps(GEOM);
+          if (NT > 0) {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            const uint64_t adesc = ad0 + geom_off16(GEOM, CIN, t);
-            const uint64_t bdesc = bd0 + static_cast<uint64_t>(t) * b_step16;
+            for (int t = 0; t < NT; ++t) {
+              const uint64_t adesc = ad0 + geom_off16(GEOM, CIN, t);
+              const uint64_t bdesc = bd0 + static_cast<uint64_t>(t) * b_step16;
 #pragma unroll
-            for (int k = 0; k < CIN / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
-          }
-        } else {
-          for (int t = 0; t < p.n_taps; ++t) {
-            const uint64_t adesc = ad0 + hp.a_tap_off16[t];
-            const uint64_t bdesc = bd0 + static_cast<uint64_t>(t) * b_step16;
+              for (int k = 0; k < CIN / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+            }
+          } else {
+            for (int t = 0; t < p.n_taps; ++t) {
+              const uint64_t adesc = ad0 + hp.a_tap_off16[t];
+              const uint64_t bdesc = bd0 + static_cast<uint64_t>(t) * b_step16;
 #pragma unroll
-            for (int k = 0; k < CIN / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+              for (int k = 0; k < CIN / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, p.idesc, (t | k) != 0);
+            }
           }
         }
+        if (leader) {
+          umma_commit(&empty[stage]);
+          umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
       }
-      if (leader) {
-        umma_commit(&empty[stage]);
-        umma_commit(&tfull[acc]);
-      }
-      __syncwarp();
       if (++stage == kAStages) {
         stage = 0;
         phase ^= 1;
@@ -1947,7 +1992,7 @@ extern "C" int dfgan_conv_run(const dfgan_conv_desc* d, dfgan_stream_t stream_) 
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<CI, GEOM>,                                      \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_halo);         \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
-    e = launch_pdl(conv_halo_kernel<CI, GEOM>, grid, kHaloThreads, smem_halo, stream, 1, maps, k, hp);       \
+    e = launch_pdl(conv_halo_kernel<CI, GEOM>, grid, kHaloNarrowThreads, smem_halo, stream, 1, maps, k, hp);       \
     if (e != cudaSuccess) return static_cast<int>(e);                                                     \
   } while (0)
 #define DFGAN_LAUNCH_HALO_C(CI)                                                                           \
