@@ -29,6 +29,10 @@ def declare(l: C.CDLL) -> None:
     l.dfgan_augment_workspace_bytes.restype = C.c_size_t
     l.dfgan_text_encoder_workspace_bytes.argtypes = [I, I]
     l.dfgan_text_encoder_workspace_bytes.restype = C.c_size_t
+    l.dfgan_peer_flag_bytes.argtypes = []
+    l.dfgan_peer_flag_bytes.restype = C.c_size_t
+    l.dfgan_peer_handle_bytes.argtypes = []
+    l.dfgan_peer_handle_bytes.restype = C.c_int
     for name, argtypes in _TABLE.items():
         fn = getattr(l, name)   # AttributeError = header and library disagree: fail loudly
         fn.argtypes = argtypes
@@ -36,6 +40,12 @@ def declare(l: C.CDLL) -> None:
 
 
 _TABLE: dict = {
+    "dfgan_peer_alloc": [C.c_size_t, P],
+    "dfgan_peer_free": [P],
+    "dfgan_peer_export": [P, P],
+    "dfgan_peer_import": [P, P],
+    "dfgan_peer_close": [P],
+    "dfgan_peer_allreduce_f32": [P, P, I, I, L, I, I, I, I, P],
     "dfgan_affine2_fwd": [P, P, P, P, P, P, L, I, I, I, P],
     "dfgan_affine2_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, L, P, P, P, I, I, I, P],
     "dfgan_pool": [P, P, P, P, F, I, I, I, I, I, F, P],
@@ -75,5 +85,5 @@ _TABLE: dict = {
 
 EXPORTS = ["dfgan_conv_run", "dfgan_wgrad_run", "dfgan_version", "dfgan_arch", "dfgan_launch_count",
            "dfgan_profile_enable", "dfgan_profile_read", "dfgan_pack_entry_size", "dfgan_pack_entry_bs_offset", "dfgan_conv_uses_image",
-           "dfgan_unpack_entry_size", "dfgan_conv_splitk_bytes", "dfgan_text_encoder_workspace_bytes", "dfgan_augment_workspace_bytes",
+           "dfgan_unpack_entry_size", "dfgan_conv_splitk_bytes", "dfgan_peer_flag_bytes", "dfgan_peer_handle_bytes", "dfgan_text_encoder_workspace_bytes", "dfgan_augment_workspace_bytes",
            *_TABLE.keys()]

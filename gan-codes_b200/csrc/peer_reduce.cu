@@ -1,0 +1,239 @@
+// Data-parallel gradient exchange over NVLink peer memory (the reference has no multi-GPU path, its
+// optimiser steps are deep_fusion_gan/model.py:195-197, 208-210, 226-228): ONE kernel all-reduces a range of the flat
+// fp32 gradient buffer across the ranks of one node -- no NCCL call, no host synchronisation, capturable in the
+// iteration's CUDA graph and small enough (no shared memory, <= 64 registers) to run next to the persistent conv
+// kernels on a side stream.
+//
+// Every rank's gradient buffer and flag block live in cudaMalloc memory exported with cudaIpcGetMemHandle and mapped
+// by the other ranks (dfgan_peer_* below), so a rank holds the address of every peer's buffer.
+//
+//   two-shot, in place:  rank r owns slice r of the range.  It (1) pulls slice r of every rank with 16-byte P2P loads,
+//   adds them in rank order 0..world-1 (one reducer per slice, fixed order: every rank ends with bit-identical sums),
+//   and (2) pushes the result into slice r of every rank with 16-byte P2P stores.  Slice r of a peer is read and written
+//   by rank r only, so nothing orders (1) against (2).
+//
+//   flags: CTA b of rank r pairs with CTA b of every peer.  START: "my gradient is final" (being launched after the
+//   producing kernels in stream order is what makes it true) is written into every peer's flag block with
+//   st.release.sys and awaited with ld.acquire.sys; END: "slice r has landed in your buffer" likewise, after a
+//   system-scope fence behind the pushes.  A rank that has seen END from every peer's CTA b for all b holds the whole
+//   reduced range, and every peer has finished reading this rank's buffer -- the caller may overwrite it again.
+//   The flag value is a per-CTA call counter kept in the local flag block (replays of a captured graph advance it).
+//
+// Waits are bounded by the global timer (a peer that died or deadlocked traps this kernel instead of hanging the box).
+#include <stdlib.h>
+#include <string.h>
+
+#include "host_common.h"
+
+namespace dfgan {
+namespace {
+
+constexpr int kMaxWorld = 8;
+constexpr int kMaxCtas = 128;
+constexpr int kChannels = 4;
+constexpr int kMaxThreads = 256;
+constexpr int kLiteThreads = 128;
+// flag block of one channel (uint32): [kMaxCtas][2 phases][kMaxWorld] flags, then [kMaxCtas] call counters
+constexpr int kFlagWords = kMaxCtas * 2 * kMaxWorld + kMaxCtas;
+
+struct PeerArgs {
+  float4* buf[kMaxWorld];       // start of the range in rank p's buffer (own buffer at [rank])
+  uint32_t* flag[kMaxWorld];    // rank p's flag block of this channel
+  int world, rank;
+  long long n4;                 // float4 elements in the range
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ float4 ld_peer(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_peer(float4* p, const float4& v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// threads 0..world-1 (except `rank`): signal peer t, then wait for peer t's signal in the local block
+__device__ __forceinline__ void pair_barrier(const PeerArgs& a, int phase, uint32_t epoch) {
+  const int t = threadIdx.x;
+  if (t < a.world && t != a.rank) {
+    const int slot = (blockIdx.x * 2 + phase) * kMaxWorld;
+    st_release_sys(a.flag[t] + slot + a.rank, epoch);
+    const uint32_t* mine = a.flag[a.rank] + slot + t;
+    const unsigned long long t0 = global_ns();
+    // signed distance: the counter may wrap after 2^32 calls
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
+      __nanosleep(64);
+      if (global_ns() - t0 > a.timeout_ns) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+// PC = peers loaded per round (loads in flight per thread = UNROLL * PC float4).  Two shapes are instantiated per world
+// size: "full" (256 threads, up to 16 loads in flight: an exposed exchange, nothing else on the SMs) and "lite"
+// (128 threads, <= 40 registers, 4 loads in flight: fits next to a resident conv_halo CTA, whose 320-352 threads x 168
+// registers leave 6-11 K registers of an SM free -- the exchange that overlaps the backward sweep).
+template <int WORLD, int UNROLL, int PC, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) peer_allreduce_kernel(const PeerArgs a) {
+  uint32_t* ctr = a.flag[a.rank] + kMaxCtas * 2 * kMaxWorld + blockIdx.x;
+  const uint32_t epoch = *ctr + 1u;
+  pair_barrier(a, 0, epoch);
+
+  const long long per = (a.n4 + WORLD - 1) / WORLD;
+  const long long lo = per * a.rank;
+  long long hi = lo + per;
+  if (hi > a.n4) hi = a.n4;
+  const int nthr = blockDim.x;
+  const long long stride = static_cast<long long>(gridDim.x) * nthr * UNROLL;
+  for (long long base = lo + static_cast<long long>(blockIdx.x) * nthr * UNROLL + threadIdx.x; base < hi;
+       base += stride) {
+    float4 s[UNROLL];
+#pragma unroll
+    for (int p0 = 0; p0 < WORLD; p0 += PC) {
+      float4 v[UNROLL][PC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long i = base + u * nthr;
+        if (i < hi) {
+#pragma unroll
+          for (int p = 0; p < PC; ++p)
+            if (p0 + p < WORLD) v[u][p] = ld_peer(a.buf[p0 + p] + i);
+        }
+      }
+      // rank order 0..WORLD-1, whatever PC is
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int p = 0; p < PC; ++p) {
+          if (p0 + p >= WORLD) continue;
+          if (p0 + p == 0) {
+            s[u] = v[u][0];
+          } else {
+            s[u].x += v[u][p].x;
+            s[u].y += v[u][p].y;
+            s[u].z += v[u][p].z;
+            s[u].w += v[u][p].w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = base + u * nthr;
+      if (i < hi) {
+#pragma unroll
+        for (int p = 0; p < WORLD; ++p) st_peer(a.buf[p] + i, s[u]);
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  pair_barrier(a, 1, epoch);
+  if (threadIdx.x == 0) *ctr = epoch;
+}
+
+template <int WORLD>
+cudaError_t launch_world(const PeerArgs& a, int ctas, int threads, cudaStream_t st) {
+  if (threads > kLiteThreads) {
+    constexpr int U = WORLD <= 2 ? 8 : (WORLD <= 4 ? 4 : 2);
+    peer_allreduce_kernel<WORLD, U, WORLD, kMaxThreads, 2><<<ctas, threads, 0, st>>>(a);
+  } else {
+    constexpr int PC = WORLD < 4 ? WORLD : 4;
+    constexpr int U = WORLD <= 2 ? 2 : 1;
+    peer_allreduce_kernel<WORLD, U, PC, kLiteThreads, 12><<<ctas, threads, 0, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+}  // namespace dfgan
+
+using namespace dfgan;
+
+extern "C" {
+
+size_t dfgan_peer_flag_bytes(void) { return static_cast<size_t>(kChannels) * kFlagWords * sizeof(uint32_t); }
+int dfgan_peer_handle_bytes(void) { return static_cast<int>(sizeof(cudaIpcMemHandle_t)); }
+
+int dfgan_peer_alloc(size_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return DFGAN_E_ARG;
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemset(*ptr, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  return static_cast<int>(e);
+}
+
+int dfgan_peer_free(void* ptr) { return static_cast<int>(cudaFree(ptr)); }
+
+int dfgan_peer_export(void* ptr, void* handle_out) {
+  if (!ptr || !handle_out) return DFGAN_E_ARG;
+  return static_cast<int>(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out), ptr));
+}
+
+int dfgan_peer_import(const void* handle, void** ptr) {
+  if (!handle || !ptr) return DFGAN_E_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  return static_cast<int>(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+}
+
+int dfgan_peer_close(void* ptr) { return static_cast<int>(cudaIpcCloseMemHandle(ptr)); }
+
+int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
+                             int ctas, int threads, int timeout_ms, dfgan_stream_t stream) {
+  if (!bufs || !flags || world < 2 || world > kMaxWorld || rank < 0 || rank >= world || count <= 0 || (count & 3) ||
+      channel < 0 || channel >= kChannels)
+    return DFGAN_E_ARG;
+  if (ctas <= 0) ctas = 32;
+  if (ctas > kMaxCtas) ctas = kMaxCtas;
+  PeerArgs a{};
+  for (int p = 0; p < world; ++p) {
+    if (!bufs[p] || !flags[p] || (reinterpret_cast<uintptr_t>(bufs[p]) & 15)) return DFGAN_E_ARG;
+    a.buf[p] = static_cast<float4*>(bufs[p]);
+    a.flag[p] = static_cast<uint32_t*>(flags[p]) + static_cast<size_t>(channel) * kFlagWords;
+  }
+  a.world = world, a.rank = rank, a.n4 = count / 4;
+  a.timeout_ns = static_cast<unsigned long long>(timeout_ms > 0 ? timeout_ms : 20000) * 1000000ull;
+  // few elements: fewer CTAs (every CTA pays two flag round trips)
+  const long long per = (a.n4 + world - 1) / world;
+  if (threads <= 0) threads = kMaxThreads;
+  threads = (threads / 32) * 32;
+  threads = threads < 32 ? 32 : (threads > kMaxThreads ? kMaxThreads : threads);
+  const long long want = (per + threads * 4 - 1) / (threads * 4);
+  if (want < ctas) ctas = static_cast<int>(want < 1 ? 1 : want);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  switch (world) {
+    case 2: e = launch_world<2>(a, ctas, threads, st); break;
+    case 3: e = launch_world<3>(a, ctas, threads, st); break;
+    case 4: e = launch_world<4>(a, ctas, threads, st); break;
+    case 5: e = launch_world<5>(a, ctas, threads, st); break;
+    case 6: e = launch_world<6>(a, ctas, threads, st); break;
+    case 7: e = launch_world<7>(a, ctas, threads, st); break;
+    default: e = launch_world<8>(a, ctas, threads, st); break;
+  }
+  if (e != cudaSuccess) return static_cast<int>(e);
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

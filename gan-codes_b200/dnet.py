@@ -193,11 +193,13 @@ def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = 
 
 
 def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: Optional[dict],
-                   need_gx: bool, cots: Optional[dict] = None) -> Optional[torch.Tensor]:
+                   need_gx: bool, cots: Optional[dict] = None, on_late=None) -> Optional[torch.Tensor]:
     """First-order backward of the trunk.  g_emb: NHWC bf16 cotangent of the embeds.  grads: name -> fp32
     accumulator (None = skip all parameter gradients, i.e. the G step / the first GP sweep).  cots (optional
     dict) receives the cotangent at every conv output for the MA-GP second sweep.  Returns d/d(image) as fp32
-    NCHW when need_gx."""
+    NCHW when need_gx.  on_late(prefix) (optional) is called on the fold-back side stream once every parameter
+    gradient of the blocks from `prefix` to the end of the trunk is final (data parallel: their exchange starts
+    there, next to the rest of the sweep); it is not called when the early fold-back is off."""
     pk.sync_late()
     dev = g_emb.device
     n = ctx["n"]
@@ -256,6 +258,8 @@ def trunk_backward(pk: DPacked, params, ctx: dict, g_emb: torch.Tensor, grads: O
                           for nm in (p_ + ".residual_conv.0.weight", p_ + ".residual_conv.2.weight")]
             with co.side(1, dev, co.POOL_AUX, after_pool=co.POOL_WGRAD):
                 pk.ws.flush(grads, late_names)
+                if on_late is not None:
+                    on_late(pk.plan[pk.first_late][0])
             flushed = set(late_names)
     if grads is not None:
         if ctx["xcol"] is None:

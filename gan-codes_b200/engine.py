@@ -33,18 +33,28 @@ STAGE_MIXED = os.environ.get("DFGAN_STAGE_MIXED", "0") == "1"
 # dist.barrier() / destroy_process_group() at teardown, so the default stays four graph segments with eager all-reduces
 # in between.
 DP_ONE_GRAPH = os.environ.get("DFGAN_DP_ONE_GRAPH", "0") == "1"
+# world > 1: "1" (default) exchanges the gradients with the library's own peer-memory all-reduce kernel (peer.py,
+# csrc/peer_reduce.cu) instead of NCCL: the kernel is captured, so N ranks replay ONE graph per iteration, and the D
+# step's low-resolution bucket (> 90 % of the bytes) is reduced on a side stream while the rest of the backward sweep
+# runs.  "0": NCCL all-reduces between graph segments (round 1).
+DP_PEER = os.environ.get("DFGAN_DP_PEER", "1") == "1"
+DP_OVERLAP = os.environ.get("DFGAN_DP_NO_OVERLAP", "0") != "1"
+PEER_OVERLAP_CTAS = int(os.environ.get("DFGAN_PEER_OVERLAP_CTAS", "128"))
 
 
 class FlatState:
     """Parameters of a module re-homed into one flat fp32 buffer (module parameters become views, so
     state_dict()/load_state_dict() keep working), with same-layout gradient and Adam-moment buffers."""
 
-    def __init__(self, module: nn.Module, lr: float, betas=(0.0, 0.9), eps: float = 1e-8, clip: float = 5.0):
+    def __init__(self, module: nn.Module, lr: float, betas=(0.0, 0.9), eps: float = 1e-8, clip: float = 5.0,
+                 peer=None):
         named = list(module.named_parameters())
         dev = named[0][1].device
         self.layout, total = ckpt.build_layout([(n, p.shape) for n, p in named])
         self.flat = torch.zeros(total, device=dev, dtype=F32)
-        self.grad = torch.zeros(total, device=dev, dtype=F32)
+        # data parallel over peer memory: the gradient buffer is the exchange buffer (mapped by every rank)
+        self.peer = peer
+        self.grad = peer.empty(total) if peer is not None else torch.zeros(total, device=dev, dtype=F32)
         self.m = torch.zeros(total, device=dev, dtype=F32)
         self.v = torch.zeros(total, device=dev, dtype=F32)
         self.params: Dict[str, torch.Tensor] = {}
@@ -66,11 +76,31 @@ class FlatState:
     def zero_grad(self) -> None:
         self.grad.zero_()
 
-    def reduce(self, world: int) -> None:
-        """Data-parallel exchange: ONE all-reduce (sum) of the flat gradient; the 1/world factor is applied
-        inside the Adam kernel.  Issued eagerly, never inside a CUDA graph."""
-        if world > 1:
-            torch.distributed.all_reduce(self.grad)
+    def offset_of(self, prefix: str) -> int:
+        """Offset (elements, a multiple of 4) of the first parameter whose name starts with `prefix`."""
+        for name, o, _ in self.layout:
+            if name.startswith(prefix):
+                return o
+        raise KeyError(prefix)
+
+    def reduce(self, world: int, lo: int = 0, hi: Optional[int] = None, channel: int = 0,
+               overlapped: bool = False) -> None:
+        """Data-parallel exchange: all-reduce (sum) of elements [lo, hi) of the flat gradient (default: all of it, ONE
+        call per optimiser step); the 1/world factor is applied inside the Adam kernel.  Peer-memory kernel on the
+        current stream (capturable) when the buffer came from a PeerGroup, else NCCL (issued eagerly).  overlapped: the
+        exchange runs next to other kernels -- the small-footprint kernel shape, one CTA per SM slot it can find."""
+        if world <= 1:
+            return
+        g = self.grad if (lo == 0 and hi is None) else self.grad[lo:hi]
+        if g.numel() == 0:
+            return
+        if self.peer is not None:
+            if overlapped:
+                self.peer.all_reduce(g, channel=channel, ctas=PEER_OVERLAP_CTAS, threads=128)
+            else:
+                self.peer.all_reduce(g, channel=channel)
+        else:
+            torch.distributed.all_reduce(g)
 
     def apply(self, world: int = 1) -> None:
         """global L2 norm -> clip -> Adam on the flat buffers (two kernels)."""
@@ -112,8 +142,12 @@ class DFGANTrainer:
             raise RuntimeError("DFGANTrainer: modules must live on a CUDA device (no CPU path)")
         self.G, self.D = generator, discriminator
         self.batch, self.world = batch, world
-        self.gs = FlatState(generator, lr_g, betas, clip=clip)
-        self.ds = FlatState(discriminator, lr_d, betas, clip=clip)
+        self.peer = None
+        if world > 1 and DP_PEER:
+            self.peer = self._peer_group(next(generator.parameters()).device)
+        self.gs = FlatState(generator, lr_g, betas, clip=clip, peer=self.peer)
+        self.ds = FlatState(discriminator, lr_d, betas, clip=clip, peer=self.peer)
+        self._d_reduced_from: Optional[int] = None
         # the reference trainer's attribute names (deep_fusion_gan/model.py:28-29, 42-43)
         self.generator, self.discriminator = generator, discriminator
         self.g_optim, self.d_optim = self.gs, self.ds
@@ -139,6 +173,27 @@ class DFGANTrainer:
         self._eager_calls = 0
         self._in = None
 
+    @staticmethod
+    def _peer_group(dev):
+        """The peer-memory exchange group, or None (-> NCCL all-reduces between graph segments) when ANY rank cannot
+        map its peers' buffers (GPUs without P2P access to each other, IPC handles refused): every rank takes the same
+        path, and the reason is printed once."""
+        import torch.distributed as dist
+        from .peer import PeerGroup
+        pg, why = None, ""
+        try:
+            pg = PeerGroup(dev)
+        except Exception as e:  # noqa: BLE001  (any failure here means "no peer memory", decided collectively below)
+            why = f"{type(e).__name__}: {e}"
+        okay = torch.tensor([1 if pg is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(okay, op=dist.ReduceOp.MIN)
+        if int(okay.item()) == 1:
+            return pg
+        if dist.get_rank() == 0 or why:
+            print(f"[dfgan] peer-memory gradient exchange unavailable ({why or 'another rank failed'}): "
+                  "falling back to ncclAllReduce between graph segments", flush=True)
+        return None
+
     # ------------------------------------------------------------------------------------ phases
     def _d_step(self, images, sent, noise):
         b = self.batch
@@ -160,8 +215,21 @@ class DFGANTrainer:
         ge, _ = dnet.head_backward(dpk, dp, hctx, g_lg, self.ds.grads, False)
         g_emb = torch.cat((ge[:b], ge[2 * b - 1:]), dim=0)
         g_emb[:b - 1] += ge[b:2 * b - 1]
-        dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_emb), self.ds.grads, False)
+        self._d_reduced_from = None
+        dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_emb), self.ds.grads, False,
+                            on_late=self._reduce_late if (self.peer is not None and DP_OVERLAP) else None)
         return loss
+
+    def _reduce_late(self, prefix: str) -> None:
+        """Called by the trunk backward on its fold-back side stream once every gradient of the low-resolution blocks
+        (from `prefix` on) and of the head is final: that tail of the flat buffer -- > 90 % of its bytes -- is
+        exchanged next to the remaining (high-resolution, long-running) part of the sweep."""
+        lo = self.ds.offset_of(prefix + ".")
+        self.ds.reduce(self.world, lo=lo, channel=1, overlapped=True)
+        self._d_reduced_from = lo
+
+    def _reduce_d_step(self) -> None:
+        self.ds.reduce(self.world, hi=self._d_reduced_from)
 
     def _d_update(self):
         self.ds.apply(self.world)
@@ -233,41 +301,42 @@ class DFGANTrainer:
 
         def s3():
             self._g_update()
-        return [(s0, self.ds), (s1, self.ds), (s2, self.gs), (s3, None)]
+        return [(s0, self._reduce_d_step), (s1, lambda: self.ds.reduce(self.world)),
+                (s2, lambda: self.gs.reduce(self.world)), (s3, None)]
 
     def _run_eager(self, images, sent, noise) -> Dict[str, torch.Tensor]:
         self._seg_out = {}
-        for fn, st in self._segments(images, sent, noise):
+        for fn, reduce in self._segments(images, sent, noise):
             fn()
-            if st is not None:
-                st.reduce(self.world)
+            if reduce is not None:
+                reduce()
         return self._seg_out
 
     def _capture(self) -> None:
         self._seg_out = {}
         segs = self._segments(*self._in)
         torch.cuda.synchronize()
-        if self.world == 1 or DP_ONE_GRAPH:
-            # data parallel: the three NCCL all-reduces are captured too (ProcessGroupNCCL supports stream capture
-            # once the communicator exists -- the eager warm-up iterations created it), so N ranks replay ONE graph
-            # per iteration exactly like one rank does.  thread_local: the NCCL watchdog thread may touch the CUDA
-            # API while this thread captures.
+        if self.world == 1 or self.peer is not None or DP_ONE_GRAPH:
+            # data parallel: the gradient exchanges are captured too -- the peer-memory kernel is an ordinary launch
+            # (with DFGAN_DP_PEER=0 DFGAN_DP_ONE_GRAPH=1: NCCL's, which ProcessGroupNCCL supports once the
+            # communicator exists) -- so N ranks replay ONE graph per iteration exactly like one rank does.
+            # thread_local: the NCCL watchdog thread may touch the CUDA API while this thread captures.
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                for fn, st in segs:
+                for fn, reduce in segs:
                     fn()
-                    if st is not None:
-                        st.reduce(self.world)
+                    if reduce is not None:
+                        reduce()
             self._graphs = [(g, None)]
         else:
             self._graphs = []
             pool = None
-            for fn, st in segs:
+            for fn, reduce in segs:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, pool=pool):
                     fn()
                 pool = g.pool()
-                self._graphs.append((g, st))
+                self._graphs.append((g, reduce))
         self._graph = self._graphs[0][0]
         self._graph_out = self._seg_out
         self.gs.frozen = self.ds.frozen = True
@@ -357,10 +426,10 @@ class DFGANTrainer:
             return self.last
         if self._graph is None:
             self._capture()
-        for g, st in self._graphs:
+        for g, reduce in self._graphs:
             g.replay()
-            if st is not None:
-                st.reduce(self.world)
+            if reduce is not None:
+                reduce()
         self.last = self._graph_out
         return self.last
 

@@ -325,6 +325,32 @@ int dfgan_augment_check(const dfgan_aug_item* item, int imsize);
 int dfgan_augment(const dfgan_aug_item* items_host, const dfgan_aug_item* items_dev, const float* lut256, float* out,
                   void* workspace, size_t ws_bytes, int B, int imsize, dfgan_stream_t st);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory (batch sharded over the GPUs of one box, the
+ * flat G / D gradients summed before clip_grad_norm_ + Adam -- the reference's optimiser steps are
+ * deep_fusion_gan/model.py:195-197, 208-210, 226-228; the reference itself is single-device).  One process per GPU.
+ *   dfgan_peer_alloc: zeroed cudaMalloc memory on the current device (the gradient buffer, the flag block of
+ *     dfgan_peer_flag_bytes() bytes); dfgan_peer_export writes its dfgan_peer_handle_bytes()-byte IPC handle, which
+ *     the caller passes to the other processes by any means; dfgan_peer_import maps a peer's handle (peer access is
+ *     enabled by the mapping); dfgan_peer_close / dfgan_peer_free undo them.
+ *   dfgan_peer_allreduce_f32: ONE kernel, in place: bufs[p] = start of the range inside rank p's buffer (bufs[rank] is
+ *     the local one, every address 16-byte aligned), flags[p] = rank p's flag block, count = fp32 elements (multiple
+ *     of 4).  Slice r of the range is summed by rank r in rank order and written to every rank, so all ranks end with
+ *     bit-identical sums.  Every rank must issue the same sequence of calls per channel (0..3; calls on different
+ *     channels may run concurrently on different streams); no host synchronisation, capturable in a CUDA graph.
+ *     ctas: grid size (<= 128, 0 = 32); threads: block size (<= 256, 0 = 256; <= 128 selects the 40-register shape
+ *     that fits on an SM next to a resident conv CTA, for an exchange overlapped with other kernels); a wait on a
+ *     peer that exceeds timeout_ms (0 = 20000) traps the kernel. */
+size_t dfgan_peer_flag_bytes(void);
+int dfgan_peer_handle_bytes(void);
+int dfgan_peer_alloc(size_t bytes, void** ptr);
+int dfgan_peer_free(void* ptr);
+int dfgan_peer_export(void* ptr, void* handle_out);
+int dfgan_peer_import(const void* handle, void** ptr);
+int dfgan_peer_close(void* ptr);
+int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
+                             int ctas, int threads, int timeout_ms, dfgan_stream_t stream);
+
 /* Per-launch timing of the two GEMM engines with CUDA events on the launching stream (bench.py roofline leg).
  * dfgan_profile_read: out[e*4 + {0: summed ms, 1: executed FLOPs, 2: algorithmic bytes, 3: launches}], e = 0 for
  * dfgan_conv_run, 1 for dfgan_wgrad_run; synchronises the device and clears the records. */
