@@ -365,7 +365,8 @@ def library_baseline(batch: int, size: int, steps: int = 5, warmup: int = 3) -> 
 
 def run_side_workload(args):
     """BASELINE configs[3] (MA-GP step, 45.51 GFLOP/img) and configs[4] (generator sampling, 15.013 GFLOP/img):
-    same harness, eager launches, device-resident inputs; one JSON line."""
+    same harness, device-resident inputs; the MA-GP step replays the trainer's CUDA graph (gradient exchange included),
+    sampling is eager launches; one JSON line."""
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -385,7 +386,7 @@ def run_side_workload(args):
     else:
         B = args.batch if args.batch != 32 else 256
         gflop = 15.013
-    trainer = DFGANTrainer(G, D, B, world=world, use_graph=False)
+    trainer = DFGANTrainer(G, D, B, world=world)
     gen = torch.Generator().manual_seed(5 + rank)
     img = (torch.randn((B, 3, 256, 256), generator=gen) * 0.5).clamp_(-1, 1).to(dev)
     sent = (torch.randn((B, 256), generator=gen) * 0.3).to(dev)

@@ -435,14 +435,42 @@ class DFGANTrainer:
 
     @torch.no_grad()
     def gp_step(self, images: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
-        """MA-GP discriminator update only (BASELINE config 4)."""
+        """MA-GP discriminator update only (BASELINE config 4): gradient penalty on the real images, backward
+        through the double-backward sweep, gradient exchange, clip + Adam (deep_fusion_gan/model.py:202-210).  Like
+        `step`: inputs are staged into static buffers, two eager calls warm up, the third captures ONE CUDA graph
+        (exchange included when it is the peer-memory kernel) that later calls replay; the returned loss is a device
+        scalar that the next call overwrites."""
         dev = self.gs.flat.device
         self._modules_stale()
-        loss = self._gp_step(images.to(dev, F32).contiguous(), sentence_embeds.to(dev, F32).contiguous())
-        self.ds.reduce(self.world)
-        self._d_update()
-        self.dpk.sync_late()
-        return loss
+        if getattr(self, "_gp_in", None) is None:
+            self._gp_in = (torch.empty(images.shape, device=dev, dtype=F32),
+                           torch.empty(sentence_embeds.shape, device=dev, dtype=F32))
+            self._gp_graph, self._gp_calls, self._gp_out = None, 0, None
+        for dst, src in zip(self._gp_in, (images, sentence_embeds)):
+            if dst.shape != src.shape:
+                raise RuntimeError(f"gp_step was first called with {tuple(dst.shape)}, got {tuple(src.shape)}")
+            dst.copy_(src, non_blocking=True)
+
+        def body():
+            loss = self._gp_step(*self._gp_in)
+            self.ds.reduce(self.world)
+            self._d_update()
+            self.dpk.sync_late()
+            return loss
+
+        graphable = self.use_graph and (self.world == 1 or self.peer is not None)
+        if not graphable or self._gp_calls < 2:
+            self._gp_calls += 1
+            return body()
+        if self._gp_graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._gp_out = body()
+            self._gp_graph = g
+            self.ds.frozen = True
+        self._gp_graph.replay()
+        return self._gp_out
 
     @torch.no_grad()
     def sample(self, noise: torch.Tensor, sentence_embeds: torch.Tensor) -> torch.Tensor:
