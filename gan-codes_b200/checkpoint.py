@@ -73,23 +73,27 @@ def load_adam_state_dict(sd: dict, layout: Layout, m: torch.Tensor, v: torch.Ten
         raise ValueError("unsupported Adam settings in checkpoint (weight_decay / amsgrad / maximize); the "
                          "reference trainer uses none of them (deep_fusion_gan/model.py:42-43)")
     state = sd["state"]
-    m.zero_()
-    v.zero_()
-    steps = set()
+    # validate everything first: a rejected checkpoint must leave the live moments untouched
+    steps, plan = set(), []
     for i, (name, o, shape) in enumerate(layout):
         st = state.get(g["params"][i])
         if st is None:          # parameter never stepped: zero moments, like a fresh torch optimiser
             steps.add(0)
             continue
-        if tuple(st["exp_avg"].shape) != tuple(shape):
-            raise ValueError(f"optimizer state of parameter {i} ({name}) has shape {tuple(st['exp_avg'].shape)}, "
-                             f"expected {tuple(shape)}")
+        for key in ("exp_avg", "exp_avg_sq"):
+            if tuple(st[key].shape) != tuple(shape):
+                raise ValueError(f"optimizer state of parameter {i} ({name}): {key} has shape "
+                                 f"{tuple(st[key].shape)}, expected {tuple(shape)}")
+        steps.add(int(float(st["step"])))
+        plan.append((o, shape, st))
+    if len(steps) > 1:
+        raise ValueError(f"per-parameter Adam step counts differ ({sorted(steps)}); the flat optimiser keeps one")
+    m.zero_()
+    v.zero_()
+    for o, shape, st in plan:
         n = shape.numel()
         m[o:o + n].view(shape).copy_(st["exp_avg"])
         v[o:o + n].view(shape).copy_(st["exp_avg_sq"])
-        steps.add(int(float(st["step"])))
-    if len(steps) > 1:
-        raise ValueError(f"per-parameter Adam step counts differ ({sorted(steps)}); the flat optimiser keeps one")
     return {"step": steps.pop() if steps else 0, "lr": float(g["lr"]),
             "betas": (float(g["betas"][0]), float(g["betas"][1])), "eps": float(g["eps"])}
 
@@ -122,11 +126,31 @@ def write_checkpoint(ck: dict, save_dir: str) -> List[str]:
     return paths + [gen]
 
 
-def read_checkpoint(path: str, map_location=None) -> dict:
-    """FileNotFoundError with the reference's message when the file is missing (:108-109)."""
+def _safe_globals() -> list:
+    """What a checkpoint of the reference's trainer holds besides tensors and builtins: numpy scalars in the loss /
+    score histories (np.mean(...) results, deep_fusion_gan/model.py:154-162)."""
+    import numpy as np
+    out = [np.dtype, np.ndarray]
+    try:
+        from numpy._core.multiarray import _reconstruct, scalar
+    except ImportError:  # numpy < 2
+        from numpy.core.multiarray import _reconstruct, scalar
+    out += [scalar, _reconstruct]
+    out += [type(np.dtype(t)) for t in ("float64", "float32", "int64", "int32", "bool")]
+    return out
+
+
+def read_checkpoint(path: str, map_location=None, trusted: bool = False) -> dict:
+    """FileNotFoundError with the reference's message when the file is missing (:108-109).  The file is read with
+    torch's restricted unpickler (tensors, containers, numpy scalars); `trusted=True` (or DFGAN_TRUSTED_CHECKPOINTS=1)
+    falls back to the unrestricted pickle load the reference uses -- only for files you wrote yourself."""
     if not os.path.exists(path):
         raise FileNotFoundError(f"Checkpoint file not found: {path}")
-    ck = torch.load(path, map_location=map_location, weights_only=False)
+    if trusted or os.environ.get("DFGAN_TRUSTED_CHECKPOINTS", "0") == "1":
+        ck = torch.load(path, map_location=map_location, weights_only=False)
+    else:
+        with torch.serialization.safe_globals(_safe_globals()):
+            ck = torch.load(path, map_location=map_location, weights_only=True)
     for k in ("epoch", "generator", "discriminator", "g_optimizer", "d_optimizer"):
         if k not in ck:
             raise KeyError(k)

@@ -484,13 +484,17 @@ __global__ void __launch_bounds__(256)
   const float coef = gscale * (max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f);
   const float c1 = 1.f - powf(b1, t), c2s = sqrtf(1.f - powf(b2, t));
   const float step_size = lr / c1;
+  // beta1 == 0 (the reference's betas = (0.0, 0.9), deep_fusion_gan/model.py:42-43): exp_avg is the clipped gradient
+  // itself -- it is still written (optimiser state_dict), but the old value is not read: 24 instead of 28 B per element
+  const bool keep_m = b1 != 0.f;
   // 16-byte accesses (the flat buffers are 16-byte aligned and padded to multiples of four elements); a scalar
   // tail covers any other caller
   const long long n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                          reinterpret_cast<uintptr_t>(v)) & 15) ? 0 : n / 4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
-    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    float4 m4 = keep_m ? reinterpret_cast<float4*>(m)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
     const float gs[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
     float* mm = reinterpret_cast<float*>(&m4);
     float* vv = reinterpret_cast<float*>(&v4);
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(256)
   }
   for (long long i = n4 * 4 + blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
     const float gi = g[i] * coef;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float mi = b1 * (keep_m ? m[i] : 0.f) + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;

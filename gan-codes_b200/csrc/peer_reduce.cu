@@ -19,6 +19,12 @@
 //   reduced range, and every peer has finished reading this rank's buffer -- the caller may overwrite it again.
 //   The flag value is a per-CTA call counter kept in the local flag block (replays of a captured graph advance it).
 //
+// In-switch variant (peer_allreduce_mc_kernel): when the buffers are bound to an NVLS multicast object (the caller maps
+// them, e.g. through torch's symmetric-memory allocator, and passes the multicast address of the range), rank r reduces
+// slice r with ONE multimem.ld_reduce per 16 bytes -- the NVSwitch reads the element from every GPU and adds on the way
+// -- and broadcasts the sum with ONE multimem.st: a GPU receives 1/N + (N-1)/N of the range instead of 2 (N-1)/N, and no
+// SM adds anything.  Same flags, same slice ownership, every rank receives the single reducer's value (bit-identical).
+//
 // Waits are bounded by the global timer (a peer that died or deadlocked traps this kernel instead of hanging the box).
 #include <stdlib.h>
 #include <string.h>
@@ -150,6 +156,52 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) peer_allreduce_kernel(con
   if (threadIdx.x == 0) *ctr = epoch;
 }
 
+__device__ __forceinline__ float4 multimem_ld_reduce(const float4* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+template <int UNROLL, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) peer_allreduce_mc_kernel(const PeerArgs a, float4* mc) {
+  uint32_t* ctr = a.flag[a.rank] + kMaxCtas * 2 * kMaxWorld + blockIdx.x;
+  const uint32_t epoch = *ctr + 1u;
+  pair_barrier(a, 0, epoch);
+
+  const long long per = (a.n4 + a.world - 1) / a.world;
+  const long long lo = per * a.rank;
+  long long hi = lo + per;
+  if (hi > a.n4) hi = a.n4;
+  const int nthr = blockDim.x;
+  const long long stride = static_cast<long long>(gridDim.x) * nthr * UNROLL;
+  for (long long base = lo + static_cast<long long>(blockIdx.x) * nthr * UNROLL + threadIdx.x; base < hi;
+       base += stride) {
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = base + u * nthr;
+      if (i < hi) v[u] = multimem_ld_reduce(mc + i);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = base + u * nthr;
+      if (i < hi) multimem_st(mc + i, v[u]);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  pair_barrier(a, 1, epoch);
+  if (threadIdx.x == 0) *ctr = epoch;
+}
+
 template <int WORLD>
 cudaError_t launch_world(const PeerArgs& a, int ctas, int threads, cudaStream_t st) {
   if (threads > kLiteThreads) {
@@ -198,28 +250,39 @@ int dfgan_peer_import(const void* handle, void** ptr) {
 
 int dfgan_peer_close(void* ptr) { return static_cast<int>(cudaIpcCloseMemHandle(ptr)); }
 
-int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
-                             int ctas, int threads, int timeout_ms, dfgan_stream_t stream) {
-  if (!bufs || !flags || world < 2 || world > kMaxWorld || rank < 0 || rank >= world || count <= 0 || (count & 3) ||
+static int peer_prepare(PeerArgs& a, void* const* flags, int world, int rank, int64_t count, int channel, int& ctas,
+                        int& threads, int timeout_ms) {
+  if (!flags || world < 2 || world > kMaxWorld || rank < 0 || rank >= world || count <= 0 || (count & 3) ||
       channel < 0 || channel >= kChannels)
     return DFGAN_E_ARG;
   if (ctas <= 0) ctas = 32;
   if (ctas > kMaxCtas) ctas = kMaxCtas;
-  PeerArgs a{};
   for (int p = 0; p < world; ++p) {
-    if (!bufs[p] || !flags[p] || (reinterpret_cast<uintptr_t>(bufs[p]) & 15)) return DFGAN_E_ARG;
-    a.buf[p] = static_cast<float4*>(bufs[p]);
+    if (!flags[p]) return DFGAN_E_ARG;
     a.flag[p] = static_cast<uint32_t*>(flags[p]) + static_cast<size_t>(channel) * kFlagWords;
   }
   a.world = world, a.rank = rank, a.n4 = count / 4;
   a.timeout_ns = static_cast<unsigned long long>(timeout_ms > 0 ? timeout_ms : 20000) * 1000000ull;
-  // few elements: fewer CTAs (every CTA pays two flag round trips)
-  const long long per = (a.n4 + world - 1) / world;
   if (threads <= 0) threads = kMaxThreads;
   threads = (threads / 32) * 32;
   threads = threads < 32 ? 32 : (threads > kMaxThreads ? kMaxThreads : threads);
+  // few elements: fewer CTAs (every CTA pays two flag round trips); the same on every rank
+  const long long per = (a.n4 + world - 1) / world;
   const long long want = (per + threads * 4 - 1) / (threads * 4);
   if (want < ctas) ctas = static_cast<int>(want < 1 ? 1 : want);
+  return 0;
+}
+
+int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
+                             int ctas, int threads, int timeout_ms, dfgan_stream_t stream) {
+  PeerArgs a{};
+  if (!bufs) return DFGAN_E_ARG;
+  const int rc = peer_prepare(a, flags, world, rank, count, channel, ctas, threads, timeout_ms);
+  if (rc) return rc;
+  for (int p = 0; p < world; ++p) {
+    if (!bufs[p] || (reinterpret_cast<uintptr_t>(bufs[p]) & 15)) return DFGAN_E_ARG;
+    a.buf[p] = static_cast<float4*>(bufs[p]);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   switch (world) {
@@ -231,6 +294,24 @@ int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, i
     case 7: e = launch_world<7>(a, ctas, threads, st); break;
     default: e = launch_world<8>(a, ctas, threads, st); break;
   }
+  if (e != cudaSuccess) return static_cast<int>(e);
+  count_launch();
+  return 0;
+}
+
+int dfgan_peer_allreduce_mc_f32(void* mc_range, void* const* flags, int world, int rank, int64_t count, int channel,
+                                int ctas, int threads, int timeout_ms, dfgan_stream_t stream) {
+  PeerArgs a{};
+  if (!mc_range || (reinterpret_cast<uintptr_t>(mc_range) & 15)) return DFGAN_E_ARG;
+  const int rc = peer_prepare(a, flags, world, rank, count, channel, ctas, threads, timeout_ms);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float4* mc = static_cast<float4*>(mc_range);
+  if (threads > kLiteThreads)
+    peer_allreduce_mc_kernel<8, kMaxThreads, 2><<<ctas, threads, 0, st>>>(a, mc);
+  else
+    peer_allreduce_mc_kernel<4, kLiteThreads, 12><<<ctas, threads, 0, st>>>(a, mc);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   count_launch();
   return 0;

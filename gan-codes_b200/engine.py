@@ -121,15 +121,19 @@ class FlatState:
                                     self.eps)
 
     def load_state_dict(self, sd: dict) -> None:
+        # every check runs before anything is written: a rejected checkpoint leaves the live optimiser as it was
+        groups = sd.get("param_groups", [])
+        if len(groups) == 1 and getattr(self, "frozen", False):
+            g = groups[0]
+            new = (float(g["lr"]), (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"]))
+            if new != (self.lr, (float(self.betas[0]), float(self.betas[1])), self.eps):
+                # hyper-parameters are launch arguments baked into a captured graph: adopt them only before capture
+                raise RuntimeError("checkpoint Adam hyper-parameters differ from the ones captured in the CUDA "
+                                   f"graph (lr {new[0]} betas {new[1]} eps {new[2]})")
         with torch.no_grad():
             h = ckpt.load_adam_state_dict(sd, self.layout, self.m, self.v)
             self.step_count.fill_(h["step"])
-        if (h["betas"], h["eps"]) != (tuple(self.betas), self.eps) or h["lr"] != self.lr:
-            # hyper-parameters are launch arguments baked into a captured graph: adopt them only before capture
-            if getattr(self, "frozen", False):
-                raise RuntimeError("checkpoint Adam hyper-parameters differ from the ones captured in the CUDA "
-                                   f"graph (lr {h['lr']} betas {h['betas']} eps {h['eps']})")
-            self.lr, self.betas, self.eps = h["lr"], h["betas"], h["eps"]
+        self.lr, self.betas, self.eps = h["lr"], h["betas"], h["eps"]
 
 
 class DFGANTrainer:

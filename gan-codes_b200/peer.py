@@ -4,7 +4,9 @@ One process per GPU.  `PeerGroup.empty(n)` is a COLLECTIVE call: e
 n elements with the library (cudaMalloc, zeroed), the IPC handles travel through `torch.distributed` (plumbing: one
 all_gather_object at set-up, nothing per iteration) and every rank maps every peer's buffer.  `all_reduce(view)` then
 launches ONE kernel on the current stream that sums the range across the ranks in place -- no NCCL call, no host
-synchronisation, capturable in the iteration's CUDA graph (engine.py).  The sum is formed by one rank per slice in
+synchronisation, capturable in the iteration's CUDA graph (engine.py).  When the NVSwitch offers multicast (NVLS) the
+buffers come from torch's symmetric-memory allocator instead (allocation + multicast binding are plumbing) and the
+kernel reduces inside the switch (`dfgan_peer_allreduce_mc_f32`).  The sum is formed by one rank per slice in
 rank order, so every rank ends with bit-identical values (what N reference replicas with summed gradients hold;
 the reference's optimiser steps: deep_fusion_gan/model.py:195-197, 208-210, 226-228).
 """
@@ -20,6 +22,10 @@ from . import _lib
 
 PEER_CTAS = int(os.environ.get("DFGAN_PEER_CTAS", "32"))
 PEER_TIMEOUT_MS = int(os.environ.get("DFGAN_PEER_TIMEOUT_MS", "20000"))
+# "1" (default): gradient buffers come from torch's symmetric-memory allocator (CUDA VMM allocations bound to an NVLS
+# multicast object when the NVSwitch supports it) and the exchange is reduced inside the switch (multimem.ld_reduce /
+# multimem.st); "0", or any rank failing to set that up: library cudaMalloc + CUDA IPC, unicast pull / push kernel.
+PEER_MULTIMEM = os.environ.get("DFGAN_PEER_MULTIMEM", "1") == "1"
 
 
 class _Raw:
@@ -31,8 +37,9 @@ class _Raw:
 
 
 class _Alloc:
-    def __init__(self, ptr: int, nbytes: int, peers: List[int]):
-        self.ptr, self.nbytes, self.peers = ptr, nbytes, peers
+    def __init__(self, ptr: int, nbytes: int, peers: List[int], mc: int = 0, owner=None):
+        # mc: multicast address of the buffer (0 = none); owner: what keeps a torch-allocated buffer alive
+        self.ptr, self.nbytes, self.peers, self.mc, self.owner = ptr, nbytes, peers, mc, owner
 
 
 class PeerGroup:
@@ -48,6 +55,7 @@ class PeerGroup:
         self.lib = _lib.lib()
         self._allocs: List[_Alloc] = []
         self._keep: list = []
+        self.multimem = PEER_MULTIMEM
         with torch.cuda.device(self.device):
             self._flags = self._alloc_shared(int(self.lib.dfgan_peer_flag_bytes()))
         self._flag_arr = (C.c_void_p * self.world)(*self._flags.peers)
@@ -93,8 +101,48 @@ class PeerGroup:
         self._allocs.append(a)
         return a
 
+    def _agree(self, ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return int(t.item()) == 1
+
+    def _empty_symm(self, numel: int) -> Optional[torch.Tensor]:
+        """Buffer from torch's symmetric-memory allocator, mapped on every rank and -- with NVLS -- bound to a multicast
+        object.  Returns None (on EVERY rank) when any rank cannot provide a multicast mapping."""
+        t, a, why = None, None, ""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else self.dist.group.WORLD
+            padded = ((numel + 3) // 4) * 4
+            t = symm.empty(padded, dtype=torch.float32, device=self.device)
+            hdl = symm.rendezvous(t, group)
+            t.zero_()
+            peers = [int(q) for q in hdl.buffer_ptrs]
+            mc = int(hdl.multicast_ptr or 0)     # 0: the allocator could not bind a multicast object
+            if mc == 0:
+                raise RuntimeError("no multicast mapping")
+            if len(peers) != self.world or peers[self.rank] != t.data_ptr():
+                raise RuntimeError("unexpected symmetric-memory pointer table")
+            a = _Alloc(t.data_ptr(), padded * 4, peers, mc, owner=(t, hdl))
+        except Exception as e:  # noqa: BLE001  (decided collectively below)
+            why = f"{type(e).__name__}: {e}"
+        if not self._agree(a is not None):
+            if self.rank == 0:
+                print(f"[dfgan] NVLS multicast buffers unavailable ({why or 'on another rank'}): CUDA IPC + unicast "
+                      "exchange", flush=True)
+            self.multimem = False
+            return None
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)
+        self._allocs.append(a)
+        return t[:numel]
+
     def empty(self, numel: int) -> torch.Tensor:
         """fp32 buffer of `numel` elements (zeroed) that every rank of the group can reach.  Collective."""
+        if self.multimem:
+            t = self._empty_symm(numel)
+            if t is not None:
+                return t
         with torch.cuda.device(self.device):
             nbytes = ((numel * 4 + 15) // 16) * 16
             a = self._alloc_shared(nbytes)
@@ -116,8 +164,14 @@ class PeerGroup:
         for a in self._allocs:
             if a.ptr <= p and p + 4 * n <= a.ptr + a.nbytes:
                 off = p - a.ptr
-                bufs = (C.c_void_p * self.world)(*[q + off for q in a.peers])
                 st = torch.cuda.current_stream(self.device).cuda_stream
+                if a.mc and self.multimem:
+                    _lib.check(self.lib.dfgan_peer_allreduce_mc_f32(C.c_void_p(a.mc + off), self._flag_arr, self.world,
+                                                                    self.rank, n, channel, ctas or PEER_CTAS, threads,
+                                                                    PEER_TIMEOUT_MS, C.c_void_p(st)),
+                               "dfgan_peer_allreduce_mc_f32")
+                    return
+                bufs = (C.c_void_p * self.world)(*[q + off for q in a.peers])
                 _lib.check(self.lib.dfgan_peer_allreduce_f32(bufs, self._flag_arr, self.world, self.rank, n, channel,
                                                              ctas or PEER_CTAS, threads, PEER_TIMEOUT_MS,
                                                              C.c_void_p(st)),
@@ -129,11 +183,12 @@ class PeerGroup:
         """Unmap the peers' buffers and free the local ones (every rank, after a device synchronisation)."""
         torch.cuda.synchronize(self.device)
         self.dist.barrier(group=self.group)
-        for a in self._allocs:
+        own = [a for a in self._allocs if a.owner is None]      # torch frees its symmetric-memory buffers itself
+        for a in own:
             for r, q in enumerate(a.peers):
                 if r != self.rank:
                     self.lib.dfgan_peer_close(C.c_void_p(q))
         self.dist.barrier(group=self.group)
-        for a in self._allocs:
+        for a in own:
             self.lib.dfgan_peer_free(C.c_void_p(a.ptr))
         self._allocs = []

@@ -102,6 +102,6 @@ class RNNEncoder(nn.Module):
     @staticmethod
     def load(weights_path: str, ntoken: int) -> "RNNEncoder":
         text_encoder = RNNEncoder(ntoken, nhidden=256)
-        state_dict = torch.load(weights_path, map_location=lambda storage, loc: storage)
+        state_dict = torch.load(weights_path, map_location="cpu", weights_only=True)   # tensors only, no pickled code
         text_encoder.load_state_dict(state_dict)
         return text_encoder

@@ -350,6 +350,12 @@ int dfgan_peer_import(const void* handle, void** ptr);
 int dfgan_peer_close(void* ptr);
 int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
                              int ctas, int threads, int timeout_ms, dfgan_stream_t stream);
+/* The same exchange reduced inside the NVSwitch: mc_range = the MULTICAST address of the range, i.e. the buffers of all
+ * ranks are bound to one NVLS multicast object at equal offsets (mapped by the caller, e.g. torch's symmetric-memory
+ * allocator: handle.multicast_ptr + byte offset).  Rank r issues one multimem.ld_reduce.add.f32 and one multimem.st per
+ * 16 bytes of slice r; flags, channels, ctas / threads / timeout_ms as above (the flag blocks stay dfgan_peer_* memory). */
+int dfgan_peer_allreduce_mc_f32(void* mc_range, void* const* flags, int world, int rank, int64_t count, int channel,
+                                int ctas, int threads, int timeout_ms, dfgan_stream_t stream);
 
 /* Per-launch timing of the two GEMM engines with CUDA events on the launching stream (bench.py roofline leg).
  * dfgan_profile_read: out[e*4 + {0: summed ms, 1: executed FLOPs, 2: algorithmic bytes, 3: launches}], e = 0 for
