@@ -150,6 +150,7 @@ class _MainProcessCollate:
         self.loader = loader
         self.dataset = dataset
         self.batch_size = loader.batch_size
+        self.sampler = loader.sampler       # DistributedSampler.set_epoch for the data-parallel trainer
 
     def __len__(self) -> int:
         return len(self.loader)
@@ -166,25 +167,32 @@ class _MainProcessCollate:
             yield self.dataset.collate(samples)
 
 
-def create_loader(imsize: int, batch_size: int, data_dir: str, split: str, num_workers: int = 0):
+def create_loader(imsize: int, batch_size: int, data_dir: str, split: str, num_workers: int = 0, rank: int = 0,
+                  world: int = 1):
     """utils.py:13-24.  `num_workers=0` is the reference's loader (one thread decodes; a seeded epoch reproduces the
     reference's batches exactly).  PIL decodes ~250 CUB photographs per second per core, a tenth of what one B200
     trains at, so production runs pass `num_workers > 0`: the JPEG decode and the caption choice move to worker
     processes, the crop / flip draws and the GPU transform stay in this process.  Sample order, crops and flips (torch
     generator of this process) are then still those of the seeded reference run; the caption picked for an image is
-    not (numpy's generator lives in the workers)."""
+    not (numpy's generator lives in the workers).  Data parallel: `rank` / `world` shard the samples with a
+    DistributedSampler (same shuffle seed on every rank, disjoint indices, `loader.sampler.set_epoch(e)` per epoch --
+    DeepFusionGAN.fit calls it)."""
     assert split in ["train", "test"], "Wrong split type, expected train or test"
     from .augment import BatchImageTransform
     dataset = DFGANDataset(data_dir, split, BatchImageTransform(imsize))
-    return make_loader(dataset, batch_size, num_workers)
+    return make_loader(dataset, batch_size, num_workers, rank, world)
 
 
-def make_loader(dataset: DFGANDataset, batch_size: int, num_workers: int = 0):
+def make_loader(dataset: DFGANDataset, batch_size: int, num_workers: int = 0, rank: int = 0, world: int = 1):
+    order = {"shuffle": True}
+    if world > 1:
+        from torch.utils.data.distributed import DistributedSampler
+        order = {"sampler": DistributedSampler(dataset, num_replicas=world, rank=rank, shuffle=True, drop_last=True)}
     if num_workers <= 0:
-        return DataLoader(dataset, batch_size=batch_size, drop_last=True, shuffle=True, collate_fn=dataset.collate)
+        return DataLoader(dataset, batch_size=batch_size, drop_last=True, collate_fn=dataset.collate, **order)
     import copy
     decode_only = copy.copy(dataset)        # what the workers receive: no transform, hence no CUDA object to fork / pickle
     decode_only.transform = None
-    return _MainProcessCollate(DataLoader(decode_only, batch_size=batch_size, drop_last=True, shuffle=True,
+    return _MainProcessCollate(DataLoader(decode_only, batch_size=batch_size, drop_last=True,
                                           collate_fn=_as_list, num_workers=num_workers, persistent_workers=True,
-                                          prefetch_factor=4), dataset)
+                                          prefetch_factor=4, **order), dataset)

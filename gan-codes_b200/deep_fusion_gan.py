@@ -130,6 +130,7 @@ class DeepFusionGAN:
         self.grad_clip_d = 5.0
         self.world = world
         self.rank = torch.distributed.get_rank() if world > 1 else 0
+        self._noise_gen = None
         self.trainer = None
         self._pin = {}
         # opt-in, not yet measured: leave the sorted image batch in pinned host memory and let DFGANTrainer.step copy
@@ -164,11 +165,29 @@ class DeepFusionGAN:
 
     def _draw_noise(self, batch_size: int) -> Tensor:
         """torch.randn(batch_size, 100).to(device) of :182 / :257 -- the same draw from the global host generator,
-        staged through two alternating pinned buffers so the copy never blocks the host."""
+        staged through two alternating pinned buffers so the copy never blocks the host.  Data parallel: every rank
+        draws from its own generator (seed of the global one + rank) -- with the documented fix_seed() on every rank
+        the global generators are identical and N ranks would otherwise train on the same latents."""
+        gen = None
+        if self.world > 1:
+            if self._noise_gen is None:
+                self._noise_gen = torch.Generator().manual_seed(torch.initial_seed() + self.rank)
+            gen = self._noise_gen
         if self.device.type != "cuda":
-            return torch.randn(batch_size, 100).to(self.device)
+            return torch.randn(batch_size, 100, generator=gen).to(self.device)
         return self._stage("noise", (batch_size, 100), torch.float32).push(
-            lambda buf: torch.randn(batch_size, 100, out=buf))
+            lambda buf: torch.randn(batch_size, 100, generator=gen, out=buf))
+
+    def _check_sharded(self, images: Tensor) -> None:
+        """Data parallel, first batch of a run: the ranks must not all hold the same images (a loader built without
+        a DistributedSampler / rank argument hands every rank the same shuffled batches, and N GPUs then compute one
+        gradient N times without anything reporting it)."""
+        probe = images.detach().double().flatten()[:: max(1, images.numel() // 4096)].sum().reshape(1).to(self.device)
+        seen = [torch.zeros_like(probe) for _ in range(self.world)]
+        torch.distributed.all_gather(seen, probe)
+        if all(torch.equal(seen[0], t) for t in seen[1:]):
+            raise RuntimeError("data parallel: every rank received the same first batch -- shard the loader "
+                               "(dataset.create_loader(..., rank=, world=) or a DistributedSampler)")
 
     def _stage(self, what: str, shape, dtype) -> _PinnedStage:
         key = (what, tuple(shape), dtype)
@@ -278,9 +297,14 @@ class DeepFusionGAN:
         say = print if self.rank == 0 else (lambda *a, **k: None)
         for epoch in trange(start_epoch, num_epochs, desc="Train Deep Fusion GAN", disable=self.rank != 0):
             sums, n_iter = None, 0
+            sampler = getattr(train_loader, "sampler", None)
+            if self.world > 1 and hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(epoch)                 # DistributedSampler: a different shuffle every epoch
             for batch in train_loader:
                 images, captions, captions_len, _ = self._prepare(batch, overlap=self._overlap_h2d)
                 batch_size = images.shape[0]
+                if self.world > 1 and epoch == start_epoch and n_iter == 0:
+                    self._check_sharded(images)
                 trainer = self._ensure_trainer(batch_size)
                 sentence_embeds = self.text_encoder(captions, captions_len).detach()            # :171
                 noise = self._draw_noise(batch_size)                                            # :182

@@ -145,3 +145,22 @@ def test_worker_processes_decode_and_the_main_process_transforms(gold):
                 assert (captions[b, n:, 0] == 0).all()
             k += 1
     assert k == 4
+
+
+def test_data_parallel_loaders_are_disjoint():
+    """create_loader(rank=, world=): the ranks of a data-parallel run read disjoint shards of one seeded shuffle, and
+    set_epoch changes the shuffle (without a sampler every rank saw the same batches)."""
+    from gan_codes_b200.dataset import make_loader
+    ds = DFGANDataset(MINI, "train", None)
+    per_rank = []
+    for rank in (0, 1):
+        ld = make_loader(ds, 1, rank=rank, world=2)
+        ld.sampler.set_epoch(0)
+        first = list(ld.sampler)
+        ld.sampler.set_epoch(1)
+        second = list(ld.sampler)
+        per_rank.append((first, second))
+    (a0, a1), (b0, b1) = per_rank
+    assert set(a0).isdisjoint(b0) and set(a1).isdisjoint(b1)
+    assert len(a0) == len(b0) == len(ds) // 2
+    assert set(a0 + b0) <= set(range(len(ds))) and (a0, b0) != (a1, b1)      # another shuffle in the next epoch
