@@ -150,25 +150,53 @@ def _check_image(img: torch.Tensor, n_blocks: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ trunk
-def trunk_forward(pk: DPacked, params, img: torch.Tensor, ctx: Optional[dict] = None,
-                  need_xcol: bool = True) -> torch.Tensor:
-    """discriminator/model.py:36-41.  img: fp32 NCHW [N,3,H,H] -> embeds NHWC bf16 [N,4,4,16*n_c].
-    ctx (optional dict) receives the activations the backward / tangent sweeps need; need_xcol=False skips the
-    im2col tensor of the stem (only its weight gradient reads it: a backward with grads=None never does)."""
+class Stem:
+    """Output of the stem convolution for a batch that arrives in parts (`stem_alloc` + `stem_run` per part): the
+    trainer's D step runs the real half on a side stream next to the generator forward and the generated half when
+    the images exist -- no [real ; fake] concatenation, and the HBM-bound stem of the real images leaves the chain."""
+
+    def __init__(self, x: torch.Tensor, xcol: Optional[torch.Tensor]):
+        self.x, self.xcol = x, xcol
+
+
+def stem_alloc(pk: DPacked, n: int, h: int, w: int, device, need_xcol: bool = True) -> Stem:
+    e = lambda *s: torch.empty(*s, device=device, dtype=BF16)  # noqa: E731
+    return Stem(e(n, h, w, pk.n_c), e(n, h, w, 32) if need_xcol else None)
+
+
+def stem_run(pk: DPacked, params, img: torch.Tensor, stem: Stem, first: int = 0) -> None:
+    """discriminator/model.py:13 (img_forward.0) on samples [first, first + len(img)) of the stem buffers."""
     _check_image(img, len(pk.plan))
-    n, _, h, w = img.shape
-    dev = img.device
-    e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
-    xcol = e(n, h, w, 32) if (ctx is not None and need_xcol) else None
-    x = e(n, h, w, pk.n_c)
+    n = img.shape[0]
+    x = stem.x[first:first + n]
+    xcol = stem.xcol[first:first + n] if stem.xcol is not None else None
+    if tuple(x.shape[1:3]) != tuple(img.shape[2:]) or x.shape[0] != n:
+        raise RuntimeError(f"stem_run: image part {tuple(img.shape)} does not fit rows [{first}, {first + n}) of "
+                           f"{tuple(stem.x.shape)}")
     if FUSED_STEM:
         _use_operand(pk.w0_f, "stem_fwd")
         K.stem_fwd(img, pk.w0_f, x, bias=params["img_forward.0.bias"], xcol=xcol)
     else:
-        if xcol is None:
-            xcol = e(n, h, w, 32)
-        K.im2col3(img, xcol)
-        co.conv_run([xcol], co.taps_1x1(), pk.w0_f, pk.n_c, x, bias=params["img_forward.0.bias"])
+        tmp = xcol if xcol is not None else torch.empty(n, x.shape[1], x.shape[2], 32, device=img.device, dtype=BF16)
+        K.im2col3(img, tmp)
+        co.conv_run([tmp], co.taps_1x1(), pk.w0_f, pk.n_c, x, bias=params["img_forward.0.bias"])
+
+
+def trunk_forward(pk: DPacked, params, img: Optional[torch.Tensor], ctx: Optional[dict] = None,
+                  need_xcol: bool = True, stem: Optional[Stem] = None) -> torch.Tensor:
+    """discriminator/model.py:36-41.  img: fp32 NCHW [N,3,H,H] -> embeds NHWC bf16 [N,4,4,16*n_c].
+    ctx (optional dict) receives the activations the backward / tangent sweeps need; need_xcol=False skips the
+    im2col tensor of the stem (only its weight gradient reads it: a backward with grads=None never does).
+    stem: the stem outputs computed beforehand (`stem_alloc` / `stem_run`), img is then ignored."""
+    if stem is None:
+        _check_image(img, len(pk.plan))
+        n, _, h, w = img.shape
+        stem = stem_alloc(pk, n, h, w, img.device, need_xcol=ctx is not None and need_xcol)
+        stem_run(pk, params, img, stem)
+    x, xcol = stem.x, stem.xcol
+    n, h, w = x.shape[0], x.shape[1], x.shape[2]
+    dev = x.device
+    e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
     saved = []
     for i, ((p, cin, cout, sc), b) in enumerate(zip(pk.plan, pk.blocks)):
         if i == pk.first_late:

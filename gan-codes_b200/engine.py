@@ -39,6 +39,7 @@ DP_ONE_GRAPH = os.environ.get("DFGAN_DP_ONE_GRAPH", "0") == "1"
 # runs.  "0": NCCL all-reduces between graph segments (round 1).
 DP_PEER = os.environ.get("DFGAN_DP_PEER", "1") == "1"
 DP_OVERLAP = os.environ.get("DFGAN_DP_NO_OVERLAP", "0") != "1"
+EARLY_REAL_STEM = os.environ.get("DFGAN_NO_EARLY_STEM", "0") != "1"    # A/B: real-image stem next to the G forward
 PEER_OVERLAP_CTAS = int(os.environ.get("DFGAN_PEER_OVERLAP_CTAS", "128"))
 
 
@@ -203,10 +204,20 @@ class DFGANTrainer:
         b = self.batch
         dp, dpk = self.ds.params, self.dpk
         self.g_ctx: dict = {}
+        # the stem of the real half does not wait for the generator: side stream, next to the generator forward;
+        # the generated half follows when the images exist (no [real ; fake] concatenation)
+        dev = images.device
+        stem = dnet.stem_alloc(dpk, 2 * b, images.shape[2], images.shape[3], dev)
+        if EARLY_REAL_STEM:
+            with co.side(2, dev, co.POOL_AUX):
+                dnet.stem_run(dpk, dp, images, stem, 0)
+        else:
+            dnet.stem_run(dpk, dp, images, stem, 0)
         fake = gnet.generator_forward(self.gpk, self.gs.params, self.mlp, noise, sent, self.g_ctx)
-        both = torch.cat((images, fake), dim=0)
+        dnet.stem_run(dpk, dp, fake, stem, b)
+        co.join(dev, co.POOL_AUX)
         tctx: dict = {}
-        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, both, tctx))         # [2B, C, 4, 4]
+        emb = dnet.embeds_to_nchw(dnet.trunk_forward(dpk, dp, None, tctx, stem=stem))         # [2B, C, 4, 4]
         emb3 = torch.cat((emb[:b], emb[:b - 1], emb[b:]), dim=0)
         sent3 = torch.cat((sent, sent[1:b], sent), dim=0)
         hctx: dict = {}

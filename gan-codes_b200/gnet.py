@@ -20,6 +20,7 @@ BF16, F32 = torch.bfloat16, torch.float32
 SENT_DIM, HID = 256, 256
 MERGE_MAX = 64   # widest phase (channels) for which the merged 9-shift launch beats four 4-tap launches
 MLPS = [(fb, m) for fb in (1, 2, 3, 4) for m in ("gamma_mlp", "beta_mlp")]
+MLP_BWD_PER_BLOCK = __import__("os").environ.get("DFGAN_MLP_BWD_WHOLE", "0") != "1"    # A/B: one launch set at the end
 
 
 def g_plan(params: Dict[str, torch.Tensor]) -> List[tuple]:
@@ -180,6 +181,26 @@ class GMlp:
         t_w1.run(self.batch)
         co.join(dev, co.POOL_AUX)
 
+    def backward_block(self, block: int) -> None:
+        """The same for the 8 MLPs of generator block `block` (plan order) alone, on a side stream: called by the
+        generator backward as soon as the block's two affine backward launches have filled its columns of d_tab, so
+        only the last block's share (and linear_in) is left behind the data-gradient chain -- as one launch over all
+        MLPs the three kernels ran alone at the end of the G step (143 us at batch 32)."""
+        t_w2, t_dd, t_w1 = self.bwd
+        per = len(MLPS)
+        dev = self.tab.device
+        with co.side(0, dev, co.POOL_AUX):     # hidden-layer cotangent -> layer-1 weight gradients
+            t_dd.run(self.batch, block * per, per)
+            t_w1.run(self.batch, block * per, per)
+        with co.side(1, dev, co.POOL_AUX):     # layer-2 weight gradients only read d_tab / hid: their own branch
+            t_w2.run(self.batch, block * per, per)
+
+    def backward_finish(self) -> None:
+        """linear_in's parameter gradients (last problem of the layer-1 table) + join of the per-block branches."""
+        t_w1 = self.bwd[2]
+        t_w1.run(self.batch, self.n_mlp, 1)
+        co.join(self.tab.device, co.POOL_AUX)
+
 
 def _phases(t: torch.Tensor):
     return [t[:, a::2, c::2, :] for a in (0, 1) for c in (0, 1)]
@@ -321,10 +342,15 @@ def generator_backward(pk: GPacked, params, mlp: GMlp, ctx: dict, g_img: torch.T
             t = pooled
         g_prev = e(n, h, h, c1)
         K.affine2_bwd(g_a12, z_prev, g_prev, mlp.tables(p, 1), mlp.tables(p, 1, mlp.d_tab), mlp.T, g_add=t)
+        if MLP_BWD_PER_BLOCK:
+            mlp.backward_block(i)
         keep += [g_z, g_h1, pooled]
         n_side += 3
         g_z = g_prev
     co.join(dev)
     pk.ws.flush(grads)
     K.nhwc_to_nchw(g_z, mlp.g_x0f.view(n, pk.c0, 4, 4))
-    mlp.backward()
+    if MLP_BWD_PER_BLOCK:
+        mlp.backward_finish()
+    else:
+        mlp.backward()

@@ -155,22 +155,30 @@ class LinearTable:
     def __init__(self, problems: Sequence[dict], mode: int, device):
         items = []
         self.k_max, self.n_out_max = 1, 1
+        self.starts = []        # first work item of every problem (run(first_problem, n_problems) launches a slice)
         for pr in problems:
             k, n_out = pr["k"], pr["n_out"]
             self.k_max, self.n_out_max = max(self.k_max, k), max(self.n_out_max, n_out)
+            self.starts.append(len(items))
             span = k if mode == 1 else n_out
             for o0 in range(0, span, 64):
                 items.append(LinearItem(pr["inp"], pr["in_stride"], pr["w"], pr.get("bias"), pr["out"],
                                         pr["out_stride"], pr.get("mask"), k, n_out, o0, int(pr.get("relu", 0))))
         self.n = len(items)
+        self.starts.append(self.n)
         arr = (LinearItem * self.n)(*items)
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         self.dev = raw.to(device)
         self.mode = mode
 
-    def run(self, batch: int) -> None:
-        _call("dfgan_linear_batched", self.dev.data_ptr(), self.n, batch, self.k_max, self.n_out_max,
-              self.mode, _s())
+    def run(self, batch: int, first_problem: int = 0, n_problems: Optional[int] = None) -> None:
+        """All work items, or those of problems [first_problem, first_problem + n_problems)."""
+        i0 = self.starts[first_problem]
+        i1 = self.n if n_problems is None else self.starts[first_problem + n_problems]
+        if i1 <= i0:
+            return
+        _call("dfgan_linear_batched", self.dev.data_ptr() + i0 * C.sizeof(LinearItem), i1 - i0, batch, self.k_max,
+              self.n_out_max, self.mode, _s())
 
 
 # ------------------------------------------------------------------------------------ packing / optimiser
