@@ -90,13 +90,15 @@ __global__ void __launch_bounds__(kLinThreads)
   const int bg = threadIdx.x >> 6;
   if (k >= it.k) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  // eight weight rows requested together (one load per FMA group left the kernel waiting on DRAM 256 times)
-  for (int o = 0; o < NO; o += 8) {
-    float w[8];
+  // sixteen weight rows requested together (one load per FMA group left the kernel waiting on DRAM 256 times; with
+  // eight in flight a 32-CTA launch -- one generator block's MLPs -- still spent 45 us on 32 dependent round trips)
+  constexpr int kRows = 16;
+  for (int o = 0; o < NO; o += kRows) {
+    float w[kRows];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) w[u] = __ldg(it.w + static_cast<long long>(o + u < NO ? o + u : o) * it.k + k);
+    for (int u = 0; u < kRows; ++u) w[u] = __ldg(it.w + static_cast<long long>(o + u < NO ? o + u : o) * it.k + k);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kRows; ++u) {
       if (o + u < NO) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(sm[(bg * 8 + j) * NO + o + u], w[u], acc[j]);

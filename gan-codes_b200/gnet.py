@@ -189,11 +189,12 @@ class GMlp:
         t_w2, t_dd, t_w1 = self.bwd
         per = len(MLPS)
         dev = self.tab.device
-        with co.side(0, dev, co.POOL_AUX):     # hidden-layer cotangent -> layer-1 weight gradients
-            t_dd.run(self.batch, block * per, per)
-            t_w1.run(self.batch, block * per, per)
-        with co.side(1, dev, co.POOL_AUX):     # layer-2 weight gradients only read d_tab / hid: their own branch
-            t_w2.run(self.batch, block * per, per)
+        # the three launches are latency-bound (32 CTAs each): consecutive blocks go to different side streams so
+        # their chains overlap instead of queueing behind one another
+        with co.side(block, dev, co.POOL_AUX):
+            t_dd.run(self.batch, block * per, per)      # hidden-layer cotangent
+            t_w1.run(self.batch, block * per, per)      # -> layer-1 weight gradients
+            t_w2.run(self.batch, block * per, per)      # layer-2 weight gradients (read d_tab / hid only)
 
     def backward_finish(self) -> None:
         """linear_in's parameter gradients (last problem of the layer-1 table) + join of the per-block branches."""
