@@ -240,7 +240,10 @@ def run_ours(args):
         p = prof[dom]
         ach = p["flops"] / (p["ms"] / 1e3) / 1e12 if p["ms"] > 0 else 0.0
         traffic = None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+        pdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+        tname = next((n for n in ("r02_traffic.json", "r01_traffic.json") if os.path.exists(os.path.join(pdir, n))),
+                     "r02_traffic.json")
+        tpath = os.path.join(pdir, tname)
         if dom == "conv" and B == 32 and os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = round(json.load(fh)["dram_bytes_per_launch"], 1)
@@ -277,7 +280,7 @@ def run_ours(args):
                          "frac": round(ach / tf_sust, 4), "traffic": traffic,
                          "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu, "
                                          "cold cache), averaged over the conv-engine launches of one iteration; "
-                                         "see profiles/r01_traffic.json",
+                                         f"see profiles/{tname}",
                          "algorithmic_bytes_per_launch": round(p["bytes"] / max(p["launches"], 1), 1),
                          "peak_source": f"{how} bf16_tflops_sustained (kernel timed inside a long step)",
                          "launches_timed": int(p["launches"]), "kernel_ms_per_step": round(p["ms"] / args.steps, 3),
