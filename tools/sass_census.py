@@ -4,7 +4,8 @@
 
 Counts, per kernel of `cuobjdump -sass`, the SASS mnemonics that prove the tcgen05 / TMEM / TMA path
 (/opt/skills/guides/B200_PROFILING.md): UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA
-tensor load / store, UBLKCP = bulk copy, plus legacy HMMA (mma.sync; expected 0) and registers from the ELF header.
+tensor load / store, UBLKCP = bulk copy, LDGMC = multimem.ld_reduce (in-switch reduction) and system-scope / multicast
+stores of the peer-memory exchange kernels, plus legacy HMMA (mma.sync; expected 0) and registers from the ELF header.
 """
 import collections
 import os
@@ -17,6 +18,7 @@ LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gan-codes_b200",
 PAT = [("UTCMMA", re.compile(r"\bUTC[A-Z]*MMA\b")), ("LDTM", re.compile(r"\bLDTM\b")), ("STTM", re.compile(r"\bSTTM\b")),
        ("UTMALDG", re.compile(r"\bUTMALDG\b")), ("UTMASTG", re.compile(r"\bUTMASTG\b")),
        ("UBLKCP", re.compile(r"\bUBLKCP\b")), ("UTCBAR", re.compile(r"\bUTCBAR\b")), ("SYNCS", re.compile(r"\bSYNCS\b")),
+       ("LDGMC", re.compile(r"\bLDGMC\b")), ("MC/SYS st", re.compile(r"\b(STG|ST)\.E\.[A-Z0-9.]*(MC|SYS)\b|\bREDG?\.[A-Z0-9.]*MC")),
        ("HMMA", re.compile(r"\bHMMA\b")), ("RED/ATOM", re.compile(r"\b(RED|REDG|ATOM|ATOMG|ATOMS)\b")), ("instr", re.compile(r"^\s+/\*[0-9a-f]{4}\*/"))]
 
 
