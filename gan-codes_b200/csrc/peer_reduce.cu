@@ -26,6 +26,7 @@
 // SM adds anything.  Same flags, same slice ownership, every rank receives the single reducer's value (bit-identical).
 //
 // Waits are bounded by the global timer (a peer that died or deadlocked traps this kernel instead of hanging the box).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -87,7 +88,11 @@ __device__ __forceinline__ void pair_barrier(const PeerArgs& a, int phase, uint3
     // signed distance: the counter may wrap after 2^32 calls
     while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
       __nanosleep(64);
-      if (global_ns() - t0 > a.timeout_ns) __trap();
+      if (global_ns() - t0 > a.timeout_ns) {
+        printf("dfgan peer exchange: rank %d CTA %d waited %llu ms for rank %d (phase %d, call %u)\n", a.rank,
+               static_cast<int>(blockIdx.x), a.timeout_ns / 1000000ull, t, phase, epoch);
+        __trap();
+      }
     }
   }
   __syncthreads();
