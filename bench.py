@@ -291,9 +291,10 @@ def run_ours(args):
                          "other_engine": {k: round(v, 3) for k, v in prof["wgrad" if dom == "conv" else "conv"].items()}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            ips, cores, total, best, kind, what = cpu_reference_step(4, S, 3, 1)
+            n_cpu = 10     # bounded sample: ~10 s of CPU work on the box's host cores
+            ips, cores, total, best, kind, what = cpu_reference_step(4, S, n_cpu, 1)
             line["cpu_baseline"] = {"value": round(ips, 4), "unit": "images/s", "cores": cores, "kind": kind,
-                                    "sample": f"3 iterations of batch 4 at {S}x{S} ({total:.1f} s) of {what}"}
+                                    "sample": f"{n_cpu} iterations of batch 4 at {S}x{S} ({total:.1f} s) of {what}"}
         if world == 1 and not args.no_library_baseline:
             del trainer
             torch.cuda.empty_cache()
