@@ -1,7 +1,11 @@
 """Multi-GPU data-parallel check (run under torchrun on N GPUs): after a few DFGANTrainer iterations on different
 shards every rank must hold bit-identical parameters (one all-reduce of the flat gradient per optimiser step, the
 same clip coefficient and Adam update everywhere), and the update must differ from a world=1 run on the same shard
-(i.e. the exchange really happened)."""
+(i.e. the exchange really happened).  With the peer-memory exchange a third run repeats the FIRST D update with the
+early (overlapped) exchange of the D step's low-resolution bucket switched off: with betas = (0, 0.9) the first Adam
+update is lr * sign(gradient), so a gradient contribution that the early exchange missed (a kernel still writing into
+the bucket) would flip the update of whole tensors, while the run-to-run noise of the fp32 atomics flips only elements
+whose gradient is ~0 -- the share of D parameters whose first update differs must stay below 1e-3."""
 import os
 import sys
 
@@ -55,6 +59,30 @@ if rank == 0:
     print(f"max |D params (world={world}) - D params (world=1, same shard)| = {diff:.3e} (must be > 0)")
     print("losses", {k: float(v) for k, v in out.items()})
 ok &= diff > 0
+from gan_codes_b200 import engine as E  # noqa: E402
+if tr.peer is not None and E.DP_OVERLAP:
+    firsts = []
+    for overlap in (True, False):
+        E.DP_OVERLAP = overlap
+        t1 = build(world)
+        start = t1.ds.flat.clone()
+        with torch.no_grad():              # the D hinge step alone: backward, exchange(s), clip + Adam
+            t1._seg_out = {}
+            d_step, d_exchange = t1._segments(img, sent, noise)[0]
+            d_step()
+            d_exchange()
+            t1.ds.apply(world)
+        torch.cuda.synchronize()
+        firsts.append((t1.ds.flat - start).clone())
+        del t1
+    E.DP_OVERLAP = True
+    a, b = firsts
+    moved = (a != 0) | (b != 0)
+    differ = float(((a - b).abs() > 1e-5 * 4e-4).logical_and(moved).sum()) / max(float(moved.sum()), 1.0)
+    if rank == 0:
+        print(f"D parameters after the first D update, early exchange on vs off: share of moved parameters whose update "
+              f"differs = {differ:.2e} (must be < 1e-3); moved {int(moved.sum())} of {moved.numel()}")
+    ok &= differ < 1e-3
 dist.barrier()
 dist.destroy_process_group()
 print(f"rank {rank}:", "DP OK" if ok else "DP MISMATCH")
