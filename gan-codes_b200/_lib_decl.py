@@ -47,6 +47,9 @@ _TABLE: dict = {
     "dfgan_peer_close": [P],
     "dfgan_peer_allreduce_f32": [P, P, I, I, L, I, I, I, I, P],
     "dfgan_peer_allreduce_mc_f32": [P, P, I, I, L, I, I, I, I, P],
+    "dfgan_peer_reduce_scatter_f32": [P, P, I, I, L, I, I, I, I, P],
+    "dfgan_peer_allgather_f32": [P, P, I, I, L, I, I, I, P],
+    "dfgan_peer_sum_scalar_f32": [P, P, P, P, I, I, I, I, P],
     "dfgan_affine2_fwd": [P, P, P, P, P, P, L, I, I, I, P],
     "dfgan_affine2_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, L, P, P, P, I, I, I, P],
     "dfgan_pool": [P, P, P, P, F, I, I, I, I, I, F, P],

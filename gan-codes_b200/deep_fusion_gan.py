@@ -353,6 +353,9 @@ class DeepFusionGAN:
                 is_scores_epoch.append(is_score)
                 fid_scores_epoch.append(fid_score)
 
+            sync = getattr(self.trainer, "sync_optimizer_state", None)
+            if self.world > 1 and sync is not None:
+                sync()      # collective; a no-op unless the optimiser step is sharded over the ranks
             if self.rank == 0:
                 self._save_fake_image_with_prompt(fake_images, captions, captions_len, epoch)
                 self._save_checkpoint(epoch, g_losses_epoch, d_losses_epoch, d_gp_losses_epoch,

@@ -39,6 +39,11 @@ DP_ONE_GRAPH = os.environ.get("DFGAN_DP_ONE_GRAPH", "0") == "1"
 # runs.  "0": NCCL all-reduces between graph segments (round 1).
 DP_PEER = os.environ.get("DFGAN_DP_PEER", "1") == "1"
 DP_OVERLAP = os.environ.get("DFGAN_DP_NO_OVERLAP", "0") != "1"
+# "1": sharded optimiser step with the peer-memory exchange: reduce-scatter of the gradient, global norm from per-rank
+# partial sums, clip + Adam on the owned slices only, all-gather of the parameters (same bytes on the links, (N-1)/N
+# of the clip + Adam passes gone from every rank).  The Adam moments are then current only on their owner:
+# DFGANTrainer.sync_optimizer_state() (collective) before a checkpoint.
+DP_SHARDED = os.environ.get("DFGAN_DP_SHARDED", "0") == "1"
 EARLY_REAL_STEM = os.environ.get("DFGAN_NO_EARLY_STEM", "0") != "1"    # A/B: real-image stem next to the G forward
 PEER_OVERLAP_CTAS = int(os.environ.get("DFGAN_PEER_OVERLAP_CTAS", "128"))
 
@@ -48,16 +53,31 @@ class FlatState:
     state_dict()/load_state_dict() keep working), with same-layout gradient and Adam-moment buffers."""
 
     def __init__(self, module: nn.Module, lr: float, betas=(0.0, 0.9), eps: float = 1e-8, clip: float = 5.0,
-                 peer=None):
+                 peer=None, sharded: bool = False):
         named = list(module.named_parameters())
         dev = named[0][1].device
         self.layout, total = ckpt.build_layout([(n, p.shape) for n, p in named])
-        self.flat = torch.zeros(total, device=dev, dtype=F32)
-        # data parallel over peer memory: the gradient buffer is the exchange buffer (mapped by every rank)
+        # data parallel over peer memory: the gradient buffer is the exchange buffer (mapped by every rank).  Sharded
+        # optimiser step (reduce-scatter -> clip + Adam on the owned slices -> all-gather of the parameters): the
+        # parameter buffer is exchanged too, and the moments are peer-mapped so that a checkpoint can collect the
+        # slices the other ranks own (sync_moments).
         self.peer = peer
+        self.sharded = bool(sharded and peer is not None)
+        shared = (lambda: peer.empty(total)) if self.sharded else (lambda: torch.zeros(total, device=dev, dtype=F32))
+        self.flat = shared()
         self.grad = peer.empty(total) if peer is not None else torch.zeros(total, device=dev, dtype=F32)
-        self.m = torch.zeros(total, device=dev, dtype=F32)
-        self.v = torch.zeros(total, device=dev, dtype=F32)
+        self.m, self.v = shared(), shared()
+        self.total = total
+        # the ranges the gradient is exchanged in (fixed for the life of the state: in the sharded step the owner of
+        # an element -- the rank that keeps its moments current -- follows from them); the trainer splits the
+        # discriminator's buffer into [low-resolution tail, head of the buffer] for the overlapped exchange
+        self.buckets = [(0, total)]
+        self._done: list = []          # buckets exchanged since the last optimiser step
+        self.moments_current = True    # sharded: False between an optimiser step and sync_moments()
+        self.partial = torch.zeros(1, device=dev, dtype=F32)
+        self._scratches: list = []
+        if self.sharded:
+            peer.enable_scalar_exchange()
         self.params: Dict[str, torch.Tensor] = {}
         self.grads: Dict[str, torch.Tensor] = {}
         with torch.no_grad():
@@ -86,30 +106,90 @@ class FlatState:
 
     def reduce(self, world: int, lo: int = 0, hi: Optional[int] = None, channel: int = 0,
                overlapped: bool = False) -> None:
-        """Data-parallel exchange: all-reduce (sum) of elements [lo, hi) of the flat gradient (default: all of it, ONE
-        call per optimiser step); the 1/world factor is applied inside the Adam kernel.  Peer-memory kernel on the
-        current stream (capturable) when the buffer came from a PeerGroup, else NCCL (issued eagerly).  overlapped: the
-        exchange runs next to other kernels -- the small-footprint kernel shape, one CTA per SM slot it can find."""
+        """Data-parallel exchange of elements [lo, hi) of the flat gradient (default: all of it; sum over the ranks,
+        the 1/world factor is applied inside the Adam kernel).  Peer-memory kernel on the current stream (capturable)
+        when the buffer came from a PeerGroup -- an all-reduce, or in the sharded step a reduce-scatter -- else NCCL
+        (issued eagerly).  overlapped: the exchange runs next to other kernels -- the small-footprint kernel shape."""
         if world <= 1:
             return
-        g = self.grad if (lo == 0 and hi is None) else self.grad[lo:hi]
+        hi = self.total if hi is None else hi
+        g = self.grad if (lo == 0 and hi == self.total) else self.grad[lo:hi]
         if g.numel() == 0:
             return
-        if self.peer is not None:
-            if overlapped:
-                self.peer.all_reduce(g, channel=channel, ctas=PEER_OVERLAP_CTAS, threads=128)
-            else:
-                self.peer.all_reduce(g, channel=channel)
-        else:
+        self._done.append((lo, hi))
+        if self.peer is None:
             torch.distributed.all_reduce(g)
+            return
+        kw = dict(channel=channel, ctas=PEER_OVERLAP_CTAS, threads=128) if overlapped else dict(channel=channel)
+        if self.sharded:
+            if (lo, hi) not in self.buckets:
+                raise RuntimeError(f"sharded optimiser step: [{lo}, {hi}) is not one of the buckets {self.buckets}")
+            self.peer.reduce_scatter(g, **kw)
+        else:
+            self.peer.all_reduce(g, **kw)
+
+    def reduce_rest(self, world: int) -> None:
+        """Exchange whatever has not been exchanged since the last optimiser step: everything in ONE call when nothing
+        has been (all-reduce path), else the remaining buckets."""
+        if world <= 1:
+            return
+        if not self._done and not self.sharded:
+            self.reduce(world)
+            return
+        for b in self.buckets:
+            if b not in self._done:
+                self.reduce(world, b[0], b[1])
 
     def apply(self, world: int = 1) -> None:
-        """global L2 norm -> clip -> Adam on the flat buffers (two kernels)."""
-        self.sumsq.zero_()
-        K.sqnorm_det(self.grad, self.sumsq, self.norm_scratch)   # bit-identical on every data-parallel rank
+        """global L2 norm -> clip -> Adam on the flat buffers (two kernels).  Sharded: the norm of the owned slices,
+        summed over the ranks in rank order, clip + Adam on the owned slices, all-gather of the parameters."""
+        done, self._done = self._done, []
+        if not (self.sharded and world > 1):
+            self.sumsq.zero_()
+            K.sqnorm_det(self.grad, self.sumsq, self.norm_scratch)   # bit-identical on every data-parallel rank
+            self.step_count.add_(1)
+            K.adam_step(self.flat, self.grad, self.m, self.v, self.sumsq, self.step_count, lr=self.lr,
+                        gscale=1.0 / world, max_norm=self.clip, b1=self.betas[0], b2=self.betas[1], eps=self.eps)
+            return
+        if sorted(done) != sorted(self.buckets):
+            raise RuntimeError(f"sharded optimiser step: exchanged {done}, buckets are {self.buckets}")
+        own = [self.peer.owned(lo, hi) for lo, hi in self.buckets]
+        self.partial.zero_()
+        while len(self._scratches) < len(own):      # one scratch per range: its layout depends on the range's grid
+            self._scratches.append(torch.zeros_like(self.norm_scratch))
+        for (lo, hi), scratch in zip(own, self._scratches):
+            if hi > lo:
+                K.sqnorm_det(self.grad[lo:hi], self.partial, scratch)
+        self.peer.sum_scalar(self.partial, self.sumsq)
         self.step_count.add_(1)
-        K.adam_step(self.flat, self.grad, self.m, self.v, self.sumsq, self.step_count, lr=self.lr,
-                    gscale=1.0 / world, max_norm=self.clip, b1=self.betas[0], b2=self.betas[1], eps=self.eps)
+        for lo, hi in own:
+            if hi > lo:
+                K.adam_step(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.sumsq,
+                            self.step_count, lr=self.lr, gscale=1.0 / world, max_norm=self.clip, b1=self.betas[0],
+                            b2=self.betas[1], eps=self.eps)
+        for lo, hi in self.buckets:
+            self.peer.all_gather(self.flat[lo:hi])
+        self.moments_current = False
+
+    def sync_moments(self) -> None:
+        """Sharded step, COLLECTIVE (every rank, outside an iteration): fetch the Adam moments of the slices the other
+        ranks own, so that state_dict() is the full optimiser state on every rank."""
+        if not self.sharded:
+            return
+        dist = torch.distributed
+        torch.cuda.synchronize(self.flat.device)
+        dist.barrier()
+        for lo, hi in self.buckets:
+            for r in range(self.peer.world):
+                if r == self.peer.rank:
+                    continue
+                olo, ohi = self.peer.owned(lo, hi, r)
+                if ohi > olo:
+                    self.m[olo:ohi].copy_(self.peer.peer_view(self.m[olo:ohi], r))
+                    self.v[olo:ohi].copy_(self.peer.peer_view(self.v[olo:ohi], r))
+        torch.cuda.synchronize(self.flat.device)
+        dist.barrier()
+        self.moments_current = True
 
     def optimizer_step(self, world: int = 1) -> None:
         self.reduce(world)
@@ -118,6 +198,9 @@ class FlatState:
     # torch.optim.Adam-compatible state (deep_fusion_gan/model.py:118-119, 305-306); reads the device step
     # counter, i.e. synchronises -- checkpoint time only, never inside an iteration
     def state_dict(self) -> dict:
+        if self.sharded and not self.moments_current:
+            raise RuntimeError("sharded optimiser step: every rank keeps only its slices of the Adam moments current; "
+                               "call DFGANTrainer.sync_optimizer_state() on ALL ranks before reading the state")
         return ckpt.adam_state_dict(self.layout, self.m, self.v, int(self.step_count.item()), self.lr, self.betas,
                                     self.eps)
 
@@ -135,6 +218,7 @@ class FlatState:
             h = ckpt.load_adam_state_dict(sd, self.layout, self.m, self.v)
             self.step_count.fill_(h["step"])
         self.lr, self.betas, self.eps = h["lr"], h["betas"], h["eps"]
+        self.moments_current = True
 
 
 class DFGANTrainer:
@@ -150,9 +234,10 @@ class DFGANTrainer:
         self.peer = None
         if world > 1 and DP_PEER:
             self.peer = self._peer_group(next(generator.parameters()).device)
-        self.gs = FlatState(generator, lr_g, betas, clip=clip, peer=self.peer)
-        self.ds = FlatState(discriminator, lr_d, betas, clip=clip, peer=self.peer)
+        self.gs = FlatState(generator, lr_g, betas, clip=clip, peer=self.peer, sharded=DP_SHARDED)
+        self.ds = FlatState(discriminator, lr_d, betas, clip=clip, peer=self.peer, sharded=DP_SHARDED)
         self._d_reduced_from: Optional[int] = None
+        self._late_bucket = False
         # the reference trainer's attribute names (deep_fusion_gan/model.py:28-29, 42-43)
         self.generator, self.discriminator = generator, discriminator
         self.g_optim, self.d_optim = self.gs, self.ds
@@ -160,6 +245,12 @@ class DFGANTrainer:
             self.gpk = gnet.GPacked(self.gs.params)
             self.dpk = dnet.DPacked(self.ds.params)
             self.mlp = gnet.GMlp(self.gs.params, self.gpk.plan, batch, self.gs.grads)
+        if self.peer is not None and DP_OVERLAP and dnet.EARLY_FLUSH and self.dpk.first_late > 0:
+            # the D gradient is exchanged in two ranges: the low-resolution tail early (next to the rest of the D
+            # step's backward sweep), the head of the buffer after the sweep
+            lo = self.ds.offset_of(self.dpk.plan[self.dpk.first_late][0] + ".")
+            self.ds.buckets = [(lo, self.ds.total), (0, lo)]
+            self._late_bucket = True
         dev = self.gs.flat.device
         co._side_streams(dev)      # created here, never inside a stream capture
         self.ones = torch.ones(batch, device=dev, dtype=F32)
@@ -232,7 +323,7 @@ class DFGANTrainer:
         g_emb[:b - 1] += ge[b:2 * b - 1]
         self._d_reduced_from = None
         dnet.trunk_backward(dpk, dp, tctx, dnet.embeds_to_nhwc(g_emb), self.ds.grads, False,
-                            on_late=self._reduce_late if (self.peer is not None and DP_OVERLAP) else None)
+                            on_late=self._reduce_late if self._late_bucket else None)
         return loss
 
     def _reduce_late(self, prefix: str) -> None:
@@ -240,11 +331,12 @@ class DFGANTrainer:
         (from `prefix` on) and of the head is final: that tail of the flat buffer -- > 90 % of its bytes -- is
         exchanged next to the remaining (high-resolution, long-running) part of the sweep."""
         lo = self.ds.offset_of(prefix + ".")
+        assert (lo, self.ds.total) == self.ds.buckets[0], (lo, self.ds.buckets)
         self.ds.reduce(self.world, lo=lo, channel=1, overlapped=True)
         self._d_reduced_from = lo
 
     def _reduce_d_step(self) -> None:
-        self.ds.reduce(self.world, hi=self._d_reduced_from)
+        self.ds.reduce_rest(self.world)
 
     def _d_update(self):
         self.ds.apply(self.world)
@@ -316,8 +408,8 @@ class DFGANTrainer:
 
         def s3():
             self._g_update()
-        return [(s0, self._reduce_d_step), (s1, lambda: self.ds.reduce(self.world)),
-                (s2, lambda: self.gs.reduce(self.world)), (s3, None)]
+        return [(s0, self._reduce_d_step), (s1, lambda: self.ds.reduce_rest(self.world)),
+                (s2, lambda: self.gs.reduce_rest(self.world)), (s3, None)]
 
     def _run_eager(self, images, sent, noise) -> Dict[str, torch.Tensor]:
         self._seg_out = {}
@@ -367,6 +459,18 @@ class DFGANTrainer:
                 cache.key = None
                 cache.packed = None
 
+    def sync_optimizer_state(self) -> None:
+        """Sharded optimiser step (DFGAN_DP_SHARDED=1, world > 1) only, COLLECTIVE: every rank collects the Adam moments
+        of the slices the other ranks keep current; afterwards checkpoint() / g_optim.state_dict() hold the full state
+        on every rank.  A no-op otherwise."""
+        for st in (self.gs, self.ds):
+            st.sync_moments()
+
+    def _moments_stale(self) -> None:
+        for st in (self.gs, self.ds):
+            if st.sharded and self.world > 1:
+                st.moments_current = False
+
     def weights_changed(self) -> None:
         """Call after writing the parameters from outside (load_state_dict, manual edits): re-packs the
         tensor-core operand copies and drops the retained generator graph."""
@@ -386,6 +490,7 @@ class DFGANTrainer:
         if images.shape[0] != self.batch:
             raise RuntimeError(f"DFGANTrainer was built for batch {self.batch}, got {images.shape[0]}")
         self._modules_stale()
+        self._moments_stale()
         if self._in is None:
             mk = lambda t: torch.empty(t.shape, device=dev, dtype=F32)  # noqa: E731
             self._in = (mk(images), mk(sentence_embeds), mk(noise))
@@ -457,6 +562,7 @@ class DFGANTrainer:
         scalar that the next call overwrites."""
         dev = self.gs.flat.device
         self._modules_stale()
+        self._moments_stale()
         if getattr(self, "_gp_in", None) is None:
             self._gp_in = (torch.empty(images.shape, device=dev, dtype=F32),
                            torch.empty(sentence_embeds.shape, device=dev, dtype=F32))
@@ -468,7 +574,7 @@ class DFGANTrainer:
 
         def body():
             loss = self._gp_step(*self._gp_in)
-            self.ds.reduce(self.world)
+            self.ds.reduce_rest(self.world)
             self._d_update()
             self.dpk.sync_late()
             return loss

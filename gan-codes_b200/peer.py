@@ -61,6 +61,7 @@ class PeerGroup:
         self._allocs: List[_Alloc] = []
         self._keep: list = []
         self.multimem = PEER_MULTIMEM == "1"
+        self._slots = None
         with torch.cuda.device(self.device):
             self._flags = self._alloc_shared(int(self.lib.dfgan_peer_flag_bytes()))
         self._flag_arr = (C.c_void_p * self.world)(*self._flags.peers)
@@ -159,30 +160,86 @@ class PeerGroup:
         return t
 
     # ------------------------------------------------------------------------------------ per iteration
+    def _locate(self, t: torch.Tensor, what: str):
+        """(allocation, byte offset) of a contiguous fp32 view into a buffer from `empty`."""
+        p, n = t.data_ptr(), t.numel()
+        if t.dtype != torch.float32 or not t.is_contiguous() or n % 4 or p % 16:
+            raise RuntimeError(f"PeerGroup.{what}: contiguous fp32 tensor, 16-byte aligned, numel % 4 == 0 expected")
+        for a in self._allocs:
+            if a.ptr <= p and p + 4 * n <= a.ptr + a.nbytes:
+                return a, p - a.ptr
+        raise RuntimeError(f"PeerGroup.{what}: tensor is not inside a buffer of this group")
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
     def all_reduce(self, t: torch.Tensor, channel: int = 0, ctas: Optional[int] = None, threads: int = 0) -> None:
         """In-place sum of `t` (a contiguous fp32 view into a buffer from `empty`, 16-byte aligned, numel % 4 == 0)
         across the ranks, on the current stream.  Every rank issues the same calls per channel in the same order.
         threads <= 128 selects the small-footprint kernel shape for an exchange that overlaps other kernels."""
-        p, n = t.data_ptr(), t.numel()
-        if t.dtype != torch.float32 or not t.is_contiguous():
-            raise RuntimeError("PeerGroup.all_reduce: contiguous fp32 tensor expected")
-        for a in self._allocs:
-            if a.ptr <= p and p + 4 * n <= a.ptr + a.nbytes:
-                off = p - a.ptr
-                st = torch.cuda.current_stream(self.device).cuda_stream
-                if a.mc and self.multimem:
-                    _lib.check(self.lib.dfgan_peer_allreduce_mc_f32(C.c_void_p(a.mc + off), self._flag_arr, self.world,
-                                                                    self.rank, n, channel, ctas or PEER_CTAS, threads,
-                                                                    PEER_TIMEOUT_MS, C.c_void_p(st)),
-                               "dfgan_peer_allreduce_mc_f32")
-                    return
-                bufs = (C.c_void_p * self.world)(*[q + off for q in a.peers])
-                _lib.check(self.lib.dfgan_peer_allreduce_f32(bufs, self._flag_arr, self.world, self.rank, n, channel,
-                                                             ctas or PEER_CTAS, threads, PEER_TIMEOUT_MS,
-                                                             C.c_void_p(st)),
-                           "dfgan_peer_allreduce_f32")
-                return
-        raise RuntimeError("PeerGroup.all_reduce: tensor is not inside a buffer of this group")
+        a, off = self._locate(t, "all_reduce")
+        n = t.numel()
+        if a.mc and self.multimem:
+            _lib.check(self.lib.dfgan_peer_allreduce_mc_f32(C.c_void_p(a.mc + off), self._flag_arr, self.world,
+                                                            self.rank, n, channel, ctas or PEER_CTAS, threads,
+                                                            PEER_TIMEOUT_MS, self._stream()),
+                       "dfgan_peer_allreduce_mc_f32")
+            return
+        bufs = (C.c_void_p * self.world)(*[q + off for q in a.peers])
+        _lib.check(self.lib.dfgan_peer_allreduce_f32(bufs, self._flag_arr, self.world, self.rank, n, channel,
+                                                     ctas or PEER_CTAS, threads, PEER_TIMEOUT_MS, self._stream()),
+                   "dfgan_peer_allreduce_f32")
+
+    # ---- sharded optimiser step: reduce-scatter -> (norm of the owned slices, summed over ranks) -> all-gather
+    def owned(self, lo: int, hi: int, rank: Optional[int] = None):
+        """[lo', hi') = the slice of elements [lo, hi) that `rank` (default: this rank) reduces / updates / pushes --
+        the partition the kernels use: ceil(n4 / world) 16-byte elements per rank."""
+        r = self.rank if rank is None else rank
+        n4 = (hi - lo) // 4
+        per = (n4 + self.world - 1) // self.world
+        return lo + 4 * min(per * r, n4), lo + 4 * min(per * (r + 1), n4)
+
+    def reduce_scatter(self, t: torch.Tensor, channel: int = 0, ctas: Optional[int] = None, threads: int = 0) -> None:
+        """Like all_reduce, but only this rank's slice of `t` (see `owned`) receives the sum; the rest of `t` keeps the
+        local values."""
+        a, off = self._locate(t, "reduce_scatter")
+        bufs = (C.c_void_p * self.world)(*[q + off for q in a.peers])
+        _lib.check(self.lib.dfgan_peer_reduce_scatter_f32(bufs, self._flag_arr, self.world, self.rank, t.numel(), channel,
+                                                          ctas or PEER_CTAS, threads, PEER_TIMEOUT_MS, self._stream()),
+                   "dfgan_peer_reduce_scatter_f32")
+
+    def all_gather(self, t: torch.Tensor, channel: int = 3, ctas: Optional[int] = None) -> None:
+        """Every rank pushes its slice of `t` into every peer's copy of `t`; when the kernel has finished, all slices
+        of all peers have landed here."""
+        a, off = self._locate(t, "all_gather")
+        bufs = (C.c_void_p * self.world)(*[q + off for q in a.peers])
+        _lib.check(self.lib.dfgan_peer_allgather_f32(bufs, self._flag_arr, self.world, self.rank, t.numel(), channel,
+                                                     ctas or PEER_CTAS, PEER_TIMEOUT_MS, self._stream()),
+                   "dfgan_peer_allgather_f32")
+
+    def sum_scalar(self, partial: torch.Tensor, total: torch.Tensor, channel: int = 2) -> None:
+        """total[0] = sum over the ranks (rank order, bit-identical everywhere) of partial[0]; device scalars."""
+        if self._slots is None:
+            raise RuntimeError("PeerGroup.sum_scalar: call enable_scalar_exchange() (collective) at set-up")
+        _lib.check(self.lib.dfgan_peer_sum_scalar_f32(C.c_void_p(partial.data_ptr()), self._slot_arr,
+                                                      C.c_void_p(total.data_ptr()), self._flag_arr, self.world, self.rank,
+                                                      channel, PEER_TIMEOUT_MS, self._stream()),
+                   "dfgan_peer_sum_scalar_f32")
+
+    def enable_scalar_exchange(self) -> None:
+        """Collective: the per-rank slot array `sum_scalar` writes into."""
+        if self._slots is None:
+            with torch.cuda.device(self.device):
+                self._slots = self._alloc_shared(64)
+            self._slot_arr = (C.c_void_p * self.world)(*self._slots.peers)
+
+    def peer_view(self, t: torch.Tensor, rank: int) -> torch.Tensor:
+        """`t` (a view into a buffer from `empty`) as stored by `rank`: a tensor over the peer-mapped address."""
+        a, off = self._locate(t, "peer_view")
+        raw = _Raw(a.peers[rank] + off, t.numel())
+        v = torch.as_tensor(raw, device=self.device)
+        self._keep.append(raw)
+        return v
 
     def close(self) -> None:
         """Unmap the peers' buffers and free the local ones (every rank, after a device synchronisation)."""

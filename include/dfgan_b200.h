@@ -336,7 +336,7 @@ int dfgan_augment(const dfgan_aug_item* items_host, const dfgan_aug_item* items_
  *   dfgan_peer_allreduce_f32: ONE kernel, in place: bufs[p] = start of the range inside rank p's buffer (bufs[rank] is
  *     the local one, every address 16-byte aligned), flags[p] = rank p's flag block, count = fp32 elements (multiple
  *     of 4).  Slice r of the range is summed by rank r in rank order and written to every rank, so all ranks end with
- *     bit-identical sums.  Every rank must issue the same sequence of calls per channel (0..3; calls on different
+ *     bit-identical sums.  Every rank must issue the same sequence of calls per channel (0..5; calls on different
  *     channels may run concurrently on different streams); no host synchronisation, capturable in a CUDA graph.
  *     ctas: grid size (<= 128, 0 = 32); threads: block size (<= 256, 0 = 256; <= 128 selects the 40-register shape
  *     that fits on an SM next to a resident conv CTA, for an exchange overlapped with other kernels); a wait on a
@@ -350,6 +350,21 @@ int dfgan_peer_import(const void* handle, void** ptr);
 int dfgan_peer_close(void* ptr);
 int dfgan_peer_allreduce_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
                              int ctas, int threads, int timeout_ms, dfgan_stream_t stream);
+/* Sharded optimiser step: the three pieces of reduce-scatter -> clip + Adam on the owned slice -> all-gather.  Slice r of
+ * a range of n4 = count / 4 16-byte elements is [per * r, min(per * (r + 1), n4)) with per = ceil(n4 / world), in all three.
+ *   dfgan_peer_reduce_scatter_f32: like dfgan_peer_allreduce_f32 without the push: rank r ends with the reduced slice r
+ *     in its own buffer (the other slices keep the local values); START rendezvous only.
+ *   dfgan_peer_sum_scalar_f32: total = sum over ranks, in rank order (bit-identical everywhere), of *partial; slots[p] =
+ *     rank p's peer-mapped array of 8 floats; one 32-thread CTA; also the rendezvous after which no rank still reads
+ *     another rank's gradient buffer.
+ *   dfgan_peer_allgather_f32: rank r pushes slice r of ITS buffer (bufs[rank]) into every peer's buffer; END rendezvous
+ *     (on return of the kernel every slice of every peer has landed locally). */
+int dfgan_peer_reduce_scatter_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count,
+                                  int channel, int ctas, int threads, int timeout_ms, dfgan_stream_t stream);
+int dfgan_peer_sum_scalar_f32(const float* partial, void* const* slots, float* total, void* const* flags, int world,
+                              int rank, int channel, int timeout_ms, dfgan_stream_t stream);
+int dfgan_peer_allgather_f32(void* const* bufs, void* const* flags, int world, int rank, int64_t count, int channel,
+                             int ctas, int timeout_ms, dfgan_stream_t stream);
 /* The same exchange reduced inside the NVSwitch: mc_range = the MULTICAST address of the range, i.e. the buffers of all
  * ranks are bound to one NVLS multicast object at equal offsets (mapped by the caller, e.g. torch's symmetric-memory
  * allocator: handle.multicast_ptr + byte offset).  Rank r issues one multimem.ld_reduce.add.f32 and one multimem.st per

@@ -60,6 +60,43 @@ if rank == 0:
     print("losses", {k: float(v) for k, v in out.items()})
 ok &= diff > 0
 from gan_codes_b200 import engine as E  # noqa: E402
+if E.DP_SHARDED and tr.peer is not None:
+    # sharded optimiser step: after the collective sync every rank holds the same, complete Adam moments, and they are
+    # those of an unsharded run up to the rounding of the differently associated norm (first update: lr * sign(g))
+    tr.sync_optimizer_state()
+    for name, st in (("G", tr.gs), ("D", tr.ds)):
+        cs = torch.stack([st.m.double().abs().sum(), st.v.double().sum()])
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        same = all(torch.equal(allcs[0], c) for c in allcs) and bool((cs > 0).all())
+        ok &= same
+        if rank == 0:
+            print(f"{name}: sharded Adam moments identical and non-zero on all ranks after sync: {same}")
+    # the FIRST D update, sharded against unsharded, from identical weights: the global squared norm (per-rank partial
+    # sums added in rank order against one pass over the whole reduced gradient) and the update itself
+    res = []
+    for sh in (True, False):
+        E.DP_SHARDED = sh
+        t1 = build(world)
+        start = t1.ds.flat.clone()
+        with torch.no_grad():
+            t1._seg_out = {}
+            d_step, d_exchange = t1._segments(img, sent, noise)[0]
+            d_step()
+            d_exchange()
+            t1.ds.apply(world)
+        torch.cuda.synchronize()
+        res.append((float(t1.ds.sumsq), (t1.ds.flat - start).clone()))
+        del t1
+    E.DP_SHARDED = True
+    (s_sh, d_sh), (s_un, d_un) = res
+    rel = abs(s_sh - s_un) / max(abs(s_un), 1e-30)
+    moved = (d_sh != 0) | (d_un != 0)
+    differ = float(((d_sh - d_un).abs() > 1e-5 * 4e-4).logical_and(moved).sum()) / max(float(moved.sum()), 1.0)
+    if rank == 0:
+        print(f"first D update, sharded vs unsharded step: |sum g^2| {s_sh:.6e} vs {s_un:.6e} (rel {rel:.1e}, must be "
+              f"< 1e-4); share of parameters whose update differs {differ:.2e} (must be < 1e-3)")
+    ok &= rel < 1e-4 and differ < 1e-3
 if tr.peer is not None and E.DP_OVERLAP:
     firsts = []
     for overlap in (True, False):
