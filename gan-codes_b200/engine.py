@@ -284,6 +284,8 @@ class DFGANTrainer:
         okay = torch.tensor([1 if pg is not None else 0], device=dev, dtype=torch.int32)
         dist.all_reduce(okay, op=dist.ReduceOp.MIN)
         if int(okay.item()) == 1:
+            if DP_SHARDED:
+                pg.multimem = False      # the sharded step's kernels are unicast: plain CUDA-IPC buffers
             return pg
         if dist.get_rank() == 0 or why:
             print(f"[dfgan] peer-memory gradient exchange unavailable ({why or 'another rank failed'}): "

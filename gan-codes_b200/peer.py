@@ -22,15 +22,14 @@ from . import _lib
 
 PEER_CTAS = int(os.environ.get("DFGAN_PEER_CTAS", "32"))
 PEER_TIMEOUT_MS = int(os.environ.get("DFGAN_PEER_TIMEOUT_MS", "20000"))
-# In-switch reduction (NVLS): "1" takes the gradient buffers from torch's symmetric-memory allocator (CUDA VMM
-# allocations bound to a multicast object) and reduces inside the NVSwitch (multimem.ld_reduce / multimem.st): a GPU
-# then moves (1 + 1/N) x the range per direction instead of 2 (N-1)/N x.  Measured with tools/peer_check.py (bit-identical
-# on all ranks, 50 graph replays): 78 MB in 195 us against 243 us unicast at 8 GPUs, but 214 us against 137 us at 2 GPUs
-# (1.5x MORE bytes there).  DEFAULT "0": inside the training iteration at 4 and 8 GPUs the eager warm-up steps of
-# bench.py ended with `unspecified launch failure` on one rank when the in-switch kernel overlapped the backward sweep
-# (2 of 2 runs; with CUDA_LAUNCH_BLOCKING=1 or DFGAN_DP_NO_OVERLAP=1 the same runs pass, 11.15 ms per iteration at 4
-# GPUs) -- not understood yet, so the unicast pull / push kernel over CUDA-IPC buffers stays the shipped path.
-PEER_MULTIMEM = os.environ.get("DFGAN_PEER_MULTIMEM", "0")
+# In-switch reduction (NVLS): the gradient buffers come from torch's symmetric-memory allocator (CUDA VMM allocations
+# bound to a multicast object) and the exchange is reduced inside the NVSwitch (multimem.ld_reduce / multimem.st): a GPU
+# then moves (1 + 1/N) x the range per direction instead of 2 (N-1)/N x.  Measured (tools/peer_check.py, bit-identical on
+# all ranks, 50 graph replays): 78 MB in 195 us against 243 us unicast at 8 GPUs, but 214 us against 137 us at 2 GPUs
+# (1.5x MORE bytes there); iteration at 4 GPUs 11.20 ms against 11.32 ms, at 8 GPUs 11.20 ms against 11.39-11.55 ms.
+# "auto" (default): in-switch from 4 ranks on; "1": at any rank count; "0", or any rank failing to set it up: library
+# cudaMalloc + CUDA IPC buffers and the unicast pull / push kernel.
+PEER_MULTIMEM = os.environ.get("DFGAN_PEER_MULTIMEM", "auto")
 
 
 class _Raw:
@@ -60,7 +59,7 @@ class PeerGroup:
         self.lib = _lib.lib()
         self._allocs: List[_Alloc] = []
         self._keep: list = []
-        self.multimem = PEER_MULTIMEM == "1"
+        self.multimem = PEER_MULTIMEM == "1" or (PEER_MULTIMEM == "auto" and self.world >= 4)
         self._slots = None
         with torch.cuda.device(self.device):
             self._flags = self._alloc_shared(int(self.lib.dfgan_peer_flag_bytes()))
