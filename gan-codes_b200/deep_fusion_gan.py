@@ -360,6 +360,10 @@ class DeepFusionGAN:
                 self._save_fake_image_with_prompt(fake_images, captions, captions_len, epoch)
                 self._save_checkpoint(epoch, g_losses_epoch, d_losses_epoch, d_gp_losses_epoch,
                                       is_scores_epoch, fid_scores_epoch, txtimg_losses_epoch)
+            if self.world > 1:
+                # rank 0 has just written files: the ranks enter the next epoch together (a rank spinning in the first
+                # gradient exchange for the length of a checkpoint write would run into the exchange kernels' wait bound)
+                torch.distributed.barrier()
             say(f"Epoch {epoch+1}: "
                   f"G Loss: {g_losses_epoch[-1]:.4f}, "
                   f"D Loss: {d_losses_epoch[-1]:.4f}, "

@@ -21,7 +21,9 @@ import torch
 from . import _lib
 
 PEER_CTAS = int(os.environ.get("DFGAN_PEER_CTAS", "32"))
-PEER_TIMEOUT_MS = int(os.environ.get("DFGAN_PEER_TIMEOUT_MS", "20000"))
+# bound of a wait on a peer inside an exchange kernel (nominal: the kernels count polls of ~0.5-1 us); generous, because a
+# rank may legitimately arrive late (first eager iteration, a checkpoint written by rank 0 between epochs)
+PEER_TIMEOUT_MS = int(os.environ.get("DFGAN_PEER_TIMEOUT_MS", "120000"))
 # In-switch reduction (NVLS): the gradient buffers come from torch's symmetric-memory allocator (CUDA VMM allocations
 # bound to a multicast object) and the exchange is reduced inside the NVSwitch (multimem.ld_reduce / multimem.st): a GPU
 # then moves (1 + 1/N) x the range per direction instead of 2 (N-1)/N x.  Measured (tools/peer_check.py, bit-identical on

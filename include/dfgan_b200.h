@@ -340,7 +340,8 @@ int dfgan_augment(const dfgan_aug_item* items_host, const dfgan_aug_item* items_
  *     channels may run concurrently on different streams); no host synchronisation, capturable in a CUDA graph.
  *     ctas: grid size (<= 128, 0 = 32); threads: block size (<= 256, 0 = 256; <= 128 selects the 40-register shape
  *     that fits on an SM next to a resident conv CTA, for an exchange overlapped with other kernels); a wait on a
- *     peer that exceeds timeout_ms (0 = 20000) traps the kernel. */
+ *     peer that exceeds about timeout_ms (0 = 20000; counted in polls of ~0.5-1 us each, not with a device timer) prints
+ *     the waiting rank / CTA / call and traps the kernel. */
 size_t dfgan_peer_flag_bytes(void);
 int dfgan_peer_handle_bytes(void);
 int dfgan_peer_alloc(size_t bytes, void** ptr);
