@@ -34,6 +34,15 @@ PEER_TIMEOUT_MS = int(os.environ.get("DFGAN_PEER_TIMEOUT_MS", "120000"))
 PEER_MULTIMEM = os.environ.get("DFGAN_PEER_MULTIMEM", "auto")
 
 
+def owned_slice(lo: int, hi: int, rank: int, world: int):
+    """[lo', hi') = the part of elements [lo, hi) of a flat fp32 buffer that `rank` of `world` reduces (reduce-scatter),
+    updates (sharded Adam) and pushes (all-gather): the partition csrc/peer_reduce.cu uses -- ceil(n4 / world) 16-byte
+    elements per rank, n4 = (hi - lo) / 4, the last ranks possibly empty."""
+    n4 = (hi - lo) // 4
+    per = (n4 + world - 1) // world
+    return lo + 4 * min(per * rank, n4), lo + 4 * min(per * (rank + 1), n4)
+
+
 class _Raw:
     """__cuda_array_interface__ carrier: lets torch view library-owned device memory without copying."""
 
@@ -195,10 +204,7 @@ class PeerGroup:
     def owned(self, lo: int, hi: int, rank: Optional[int] = None):
         """[lo', hi') = the slice of elements [lo, hi) that `rank` (default: this rank) reduces / updates / pushes --
         the partition the kernels use: ceil(n4 / world) 16-byte elements per rank."""
-        r = self.rank if rank is None else rank
-        n4 = (hi - lo) // 4
-        per = (n4 + self.world - 1) // self.world
-        return lo + 4 * min(per * r, n4), lo + 4 * min(per * (r + 1), n4)
+        return owned_slice(lo, hi, self.rank if rank is None else rank, self.world)
 
     def reduce_scatter(self, t: torch.Tensor, channel: int = 0, ctas: Optional[int] = None, threads: int = 0) -> None:
         """Like all_reduce, but only this rank's slice of `t` (see `owned`) receives the sum; the rest of `t` keeps the

@@ -94,3 +94,19 @@ def test_two_rank_gloo_equals_averaged_replicas(tmp_path):
         assert float((r0["g"][k] - v).abs().max()) <= 1e-9 * (1 + float(v.abs().max())), k
     for k, v in d_ref.items():
         assert float((r0["d"][k] - v).abs().max()) <= 1e-9 * (1 + float(v.abs().max())), k
+
+
+def test_owned_slices_partition_a_bucket():
+    """Host side of the sharded optimiser step: the slices the ranks own (gan_codes_b200.peer.owned_slice, the
+    partition csrc/peer_reduce.cu computes per kernel) tile every bucket exactly, in rank order, on 16-byte boundaries."""
+    from gan_codes_b200.peer import owned_slice
+    for lo, hi in ((0, 19_645_272), (1_529_728, 19_645_272), (0, 1_529_728), (8, 12), (0, 4), (16, 16 + 4 * 7)):
+        for world in (2, 3, 4, 5, 8):
+            at = lo
+            for r in range(world):
+                a, b = owned_slice(lo, hi, r, world)
+                assert a == at and a <= b <= hi and (a - lo) % 4 == 0 and (b - lo) % 4 == 0
+                at = b
+            assert at == hi
+            per = 4 * (((hi - lo) // 4 + world - 1) // world)
+            assert all(owned_slice(lo, hi, r, world)[1] - owned_slice(lo, hi, r, world)[0] <= per for r in range(world))
