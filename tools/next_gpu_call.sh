@@ -1,14 +1,12 @@
 #!/usr/bin/env bash
-# First GPU call of the next round: everything that was written after round 1's GPU budget was spent, in one gpurun.
-#   gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh'
-# Outputs land in gpurun_out/ (copy what is to be judged into profiles/).
+# First GPU calls of the next round (what round 2 could not re-measure after its GPU budget was spent):
+#   gpurun --timeout 900 -- 'bash tools/run_evidence_1gpu.sh'          pytest -m gpu, bench line with both baselines,
+#                                                                       per-launch table, timeline (one B200)
+#   gpurun --gpus 8 --timeout 600 -- 'bash tools/run_peer_8gpu.sh'      in-switch exchange at 8 GPUs: kernel check,
+#                                                                       trainer check, iteration bench (in-switch / unicast)
+#   gpurun --gpus 4 --timeout 600 -- 'bash tools/run_dp_4gpu.sh'        4 GPUs: default / in-switch / sharded step
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/run_sharded_2gpu.sh'   2 GPUs: dp_check (default, sharded), benches
+# Open items with a measured starting point: narrow-layer tap stacking, Adam + re-pack fusion,
+# bucketed exchange of the generator's gradient, sharded step with the pull and push overlapped.
 set -u
-mkdir -p gpurun_out
-python tools/bringup_configs.py                    > gpurun_out/configs.log    2>&1; echo "configs rc=$?"
-python tools/prof_shell.py --overlap 0             > gpurun_out/prof_shell0.json 2> gpurun_out/prof_shell0.err; echo "prof_shell overlap=0 rc=$?"
-python tools/prof_shell.py --overlap 1             > gpurun_out/prof_shell1.json 2> gpurun_out/prof_shell1.err; echo "prof_shell overlap=1 rc=$?"
-python -m pytest tests -m gpu -x -q                > gpurun_out/pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?"
-python bench.py --steps 20 --warmup 5              > gpurun_out/bench.json     2> gpurun_out/bench.err; echo "bench rc=$?"
-tail -3 gpurun_out/configs.log gpurun_out/pytest_gpu.log
-cat gpurun_out/prof_shell0.json gpurun_out/prof_shell1.json
-cut -c1-300 gpurun_out/bench.json
+bash tools/run_evidence_1gpu.sh
