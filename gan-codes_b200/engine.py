@@ -16,6 +16,7 @@ No host synchronisation happens inside `step`; losses are returned as device sca
 from __future__ import annotations
 
 import os
+import sys
 from typing import Dict, Optional
 
 import torch
@@ -289,7 +290,7 @@ class DFGANTrainer:
             return pg
         if dist.get_rank() == 0 or why:
             print(f"[dfgan] peer-memory gradient exchange unavailable ({why or 'another rank failed'}): "
-                  "falling back to ncclAllReduce between graph segments", flush=True)
+                  "falling back to ncclAllReduce between graph segments", file=sys.stderr, flush=True)
         return None
 
     # ------------------------------------------------------------------------------------ phases

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import List, Optional
 
 import torch
@@ -145,7 +146,7 @@ class PeerGroup:
         if not self._agree(a is not None):
             if self.rank == 0:
                 print(f"[dfgan] NVLS multicast buffers unavailable ({why or 'on another rank'}): CUDA IPC + unicast "
-                      "exchange", flush=True)
+                      "exchange", file=sys.stderr, flush=True)
             self.multimem = False
             return None
         torch.cuda.synchronize(self.device)
