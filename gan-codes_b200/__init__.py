@@ -11,6 +11,8 @@ Reference-facing modules (same names / signatures as the reference's classes and
   damsm, sample, train   damsm_loss; generate_images / save_image / sample; fix_seed / train
 Engine underneath:
   engine           DFGANTrainer (fused iteration, CUDA graph, data parallel), FlatState (flat Adam)
+  peer             PeerGroup: gradient buffers mapped across the ranks of one box (CUDA IPC / NVLS multicast) and the
+                   exchange kernels over them (all-reduce, in-switch all-reduce, reduce-scatter / all-gather)
   gnet, dnet, convops, kernels, fp32, checkpoint, _lib (ctypes binding of include/dfgan_b200.h)
 """
 __version__ = "0.1.0"
